@@ -1,0 +1,210 @@
+/*
+ * vps_b200.h -- C ABI of libvps_b200.so (sm_100a kernels for the FuseTrack frame-pair path).
+ *
+ * Every entry point takes plain device pointers, sizes and a cudaStream_t (as void*), returns an
+ * int status (0 = ok, negative = VPS_E_*), never throws across the ABI and never frees caller
+ * memory.  Each declaration cites the reference interface (file:line under mcahny/vps) it replaces.
+ *
+ * Tensor convention (differs from the reference on purpose): activations are NHWC ("pixel-major")
+ * with an explicit per-pixel channel stride `cs`, so a channel slice of a concat buffer is a view
+ * (ptr + c_off, cs = total channels).  address(n,y,x,c) = ptr + ((n*h + y)*w + x)*cs + c.
+ * dtype: VPS_F32 or VPS_BF16.  The boundary tensors of the detector (images in, label maps out)
+ * stay NCHW fp32 / int64 exactly as in the reference; the layout conversion is one kernel each way.
+ */
+#ifndef VPS_B200_H_
+#define VPS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPS_OK 0
+#define VPS_E_ARG (-1)     /* bad argument / unsupported geometry */
+#define VPS_E_CUDA (-2)    /* a CUDA runtime / driver call failed (see vps_last_error) */
+#define VPS_E_NODEV (-3)   /* no sm_100 device */
+
+#define VPS_F32 0
+#define VPS_BF16 1
+
+#define VPS_ACT_NONE 0
+#define VPS_ACT_RELU 1
+#define VPS_ACT_LRELU 2    /* negative slope in vps_conv_args.slope (reference uses 0.1) */
+#define VPS_ACT_SIGMOID 3
+
+typedef struct vps_tensor {
+  void* ptr;
+  int32_t n, h, w, c;   /* logical NHWC extent */
+  int32_t cs;           /* channel stride: elements between consecutive pixels (>= c) */
+  int32_t dtype;        /* VPS_F32 | VPS_BF16 */
+} vps_tensor;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* vps_last_error(void);
+int vps_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
+int64_t vps_launch_count(void);
+
+/* ---- dense contractions -------------------------------------------------------------------- */
+/*
+ * Convolution as implicit GEMM.  Replaces every nn.Conv2d / ConvTranspose2d / nn.Linear call on
+ * the path (cuDNN/cuBLAS in the reference; e.g. resnet.py:506-517, fpn.py:100-139,
+ * tcea_modules.py:50-78, FlowNetS.py:62-94, convfc_bbox_head.py:132-168, fcn_mask_head.py:94-103)
+ * and the GEMM half of DCNv1 (deform_conv_cuda.cpp:231-236).
+ *
+ *   y[n, oy*oy_mul+oy_off, ox*ox_mul+ox_off, co] =
+ *       act( bias[co] + sum_{r,s,ci} x[n, oy*sh - ph + r, ox*sw - pw + s, ci] * W[co,r,s,ci] ) (+ res)
+ *
+ * for oy < oh, ox < ow.  Out-of-range input taps read zero.  (oy_mul,oy_off,...) let a transposed
+ * convolution run as stride-phase sub-convolutions writing interleaved output pixels.
+ *
+ * vps_conv2d_tc   : bf16 operands, fp32 accumulation on tcgen05 tensor cores (TMA im2col tiles,
+ *                   accumulators in TMEM).  w = bf16 [cout_pad][kh*kw*cin_pad] (ci fastest,
+ *                   cin_pad = cin rounded up to 64, cout_pad to 16), produced by vps_pack_weights_tc.
+ *                   x must be VPS_BF16 with cs % 8 == 0 and 16-byte aligned ptr.
+ * vps_conv2d_simt : fp32 (or bf16 storage) direct convolution on CUDA cores with fp32 FMA --
+ *                   the parity-mode path and the path for tiny channel counts.
+ *                   w = f32 [kh][kw][cin][cout].
+ */
+typedef struct vps_conv_args {
+  vps_tensor x, y, res;       /* res.ptr == NULL: no residual.  res is added AFTER act when
+                                 res_after_act != 0, else before (ResNet: add then ReLU). */
+  const void* w;
+  const float* bias;          /* [cout] fp32 or NULL */
+  int32_t kh, kw, sh, sw, ph, pw;
+  int32_t oh, ow;
+  int32_t oy_mul, oy_off, ox_mul, ox_off;
+  int32_t cin, cout;
+  int32_t act;
+  float slope;
+  int32_t res_after_act;
+  float out_scale;            /* y = out_scale * act(...) ; 1.0 normally (FlowNet2 div_flow folds here) */
+} vps_conv_args;
+
+int vps_conv2d_tc(const vps_conv_args* a, void* stream);
+int vps_conv2d_simt(const vps_conv_args* a, void* stream);
+/* OIHW fp32 (torch layout, on device) -> packed layouts.  scale[cout] (may be NULL) is folded in
+ * (frozen BatchNorm: resnet.py:519-526).  transposed != 0: src is IOHW (ConvTranspose2d). */
+int vps_pack_weights_tc(const float* w_oihw, const float* scale, void* dst_bf16, int cout, int cin,
+                        int kh, int kw, int transposed, void* stream);
+int vps_pack_weights_simt(const float* w_oihw, const float* scale, float* dst, int cout, int cin,
+                          int kh, int kw, int transposed, void* stream);
+/* bytes of the packed tc weight buffer */
+int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw);
+
+/* explicit im2col for small-cin layers feeding vps_conv2d_tc as a 1x1 conv: cols is NHWC
+ * [n, oh, ow, kpad] with k = (r*kw+s)*cin + ci, zero padded to cols.c. */
+int vps_im2col(const vps_tensor* x, const vps_tensor* cols, int kh, int kw, int sh, int sw, int ph,
+               int pw, void* stream);
+
+/* ---- FlowNet2 native ops --------------------------------------------------------------------- */
+/* correlation_cuda.forward (correlation_cuda.cc:10-87, correlation_cuda_kernel.cu:74-147),
+ * kernel_size 1.  out channel (tj+R)*D+(ti+R), R = max_disp/stride2, D = 2R+1; out = sum_c / C.
+ * Optional fused LeakyReLU (FlowNetC.py:33,87).  f1,f2,out NHWC. */
+int vps_correlation(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
+                    int max_disp, int stride1, int stride2, int act, float slope, void* stream);
+/* resample2d_cuda.forward (resample2d_cuda.cc:6-31, resample2d_kernel.cu:16-71): bilinear warp by
+ * pixel-unit flow (channel 0 = x), border-clamped taps, kernel_size 1. */
+int vps_resample2d(const vps_tensor* src, const vps_tensor* flow, const vps_tensor* out, void* stream);
+/* channelnorm_cuda.forward (channelnorm_cuda.cc:6-30, channelnorm_kernel.cu:19-60): sqrt(sum_c x^2);
+ * computes the norm of (a - b) when b != NULL (fuses flownet2.py:147-148). out has 1 channel. */
+int vps_channelnorm(const vps_tensor* a, const vps_tensor* b, const vps_tensor* out, void* stream);
+
+/* ---- layout / pointwise / resampling --------------------------------------------------------- */
+int vps_nchw_to_nhwc(const float* src, const vps_tensor* dst, void* stream);   /* src [n,c,h,w] f32 */
+int vps_nhwc_to_nchw(const vps_tensor* src, float* dst, void* stream);
+/* dst = alpha * src (+ beta) channel-slice copy with dtype conversion */
+int vps_copy_scale(const vps_tensor* src, const vps_tensor* dst, float alpha, void* stream);
+/* out = a*alpha + b*beta (b may be NULL) */
+int vps_axpby(const vps_tensor* a, const vps_tensor* b, const vps_tensor* out, float alpha, float beta,
+              void* stream);
+/* F.interpolate bilinear align_corners=False (torch semantics incl. scale = in/out), out size from `out`;
+ * result multiplied by `mul` (panoptic_fusetrack.py:141-142, upsnetFPN.py:74-80, flownet2.py:45,57). */
+int vps_resize_bilinear(const vps_tensor* src, const vps_tensor* out, float mul, void* stream);
+/* F.interpolate nearest: src index = floor(dst * in/out) (fpn.py:112-113, flownet2.py:72-73);
+ * accumulate != 0: out += (FPN top-down add). */
+int vps_resize_nearest(const vps_tensor* src, const vps_tensor* out, float mul, int accumulate, void* stream);
+/* max / avg pool (resnet.py:451, tcea_modules.py:27-28; avg = count_include_pad) */
+int vps_pool2d(const vps_tensor* src, const vps_tensor* out, int k, int s, int p, int is_avg, void* stream);
+/* GroupNorm(groups, eps) + optional ReLU (upsnetFPN.py:42-51) */
+int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const float* gamma, const float* beta, int groups,
+                  float eps, int relu, void* stream);
+
+/* ---- BFPTcea -------------------------------------------------------------------------------- */
+/* gather: mean over levels of nearest-upsampled maps (bfp_tcea.py:96-109), refine_level 0 */
+int vps_bfp_gather(const vps_tensor* levels, int nlev, const vps_tensor* out, void* stream);
+/* scatter: out_i = adaptive_max_pool2d(bsf, size_i) + in_i (bfp_tcea.py:141-147) */
+int vps_bfp_scatter(const vps_tensor* bsf, const vps_tensor* in, const vps_tensor* out, void* stream);
+/* WarpingLayer (flow_modules.py:126-148): grid_sample(bilinear, zeros, align_corners=False) at
+ * ix = (x + fx) * W/(W-1) - 0.5 */
+int vps_flow_warp(const vps_tensor* src, const vps_tensor* flow, const vps_tensor* out, void* stream);
+/* TCEA temporal attention (tcea_modules.py:52-61): out[:, f*C:(f+1)*C] = fea_f * sigmoid(sum_c emb_f*emb_ref) */
+int vps_tcea_temporal(const vps_tensor* fea0, const vps_tensor* fea1, const vps_tensor* emb0,
+                      const vps_tensor* emb1, const vps_tensor* emb_ref, const vps_tensor* out, void* stream);
+/* fea * sigmoid(att) * 2 + att_add (tcea_modules.py:75-77) */
+int vps_tcea_combine(const vps_tensor* fea, const vps_tensor* att, const vps_tensor* att_add,
+                     const vps_tensor* out, void* stream);
+
+/* ---- DCNv1 ---------------------------------------------------------------------------------- */
+/* deformable_im2col (deform_conv_cuda_kernel.cu:83-113,189-242), 3x3 stride 1 pad 1 dil 1,
+ * deformable_group 1.  offset NHWC [n,h,w,18] (ch 2k = dy, 2k+1 = dx); cols NHWC [n,h,w,9*c] (k-major). */
+int vps_deform_im2col(const vps_tensor* x, const vps_tensor* offset, const vps_tensor* cols, void* stream);
+
+/* ---- detection ops --------------------------------------------------------------------------- */
+/* RoIAlign legacy mmdet v1 (roi_align_kernel.cu:16-128) with FPN level mapping
+ * (single_level.py:54-73, finest_scale 56).  feats: nlev NHWC maps, strides[nlev]; rois device
+ * f32 [nroi,5]; out NHWC [nroi, ps, ps, c].  nroi_dev (may be NULL) = device int holding the valid count. */
+int vps_roi_align(const vps_tensor* feats, const int* strides, int nlev, const float* rois, int nroi,
+                  const int* nroi_dev, const vps_tensor* out, int sample_num, void* stream);
+/* stable descending sort of keys with payload indices; n <= 2^20 (segmented: nseg segments of
+ * length seglen).  Outputs sorted keys + original indices; top-k = prefix. */
+int vps_sort_desc(const float* keys, float* keys_out, int32_t* idx_out, int n, void* ws, int64_t ws_bytes,
+                  void* stream);
+/* RPN per-level candidate decode (rpn_head.py:66-85 + delta2bbox transforms.py:34-68):
+ * for the top `k` sorted indices: anchor from index, decode, clamp; writes dets [k,5] (x1,y1,x2,y2,score). */
+int vps_rpn_decode(const float* scores_sorted, const int32_t* idx_sorted, int k, const vps_tensor* deltas,
+                   int feat_h, int feat_w, int stride, const float* base_anchors, int num_anchors,
+                   float img_h, float img_w, float* dets, void* stream);
+/* greedy NMS (nms_kernel.cu:13-131): dets [n,5] sorted by score desc; IoU with +1 extents, suppress when
+ * IoU > thr.  Entirely on device: keep_idx[0..*nkeep) ascending (== score order).  n may be read from n_dev. */
+int vps_nms(const float* dets, int n, const int* n_dev, float thr, int32_t* keep_idx, int* nkeep,
+            void* ws, int64_t ws_bytes, void* stream);
+/* sigmoid on a flat NHWC map flattened to the reference's (h, w, a) order is the identity layout. */
+int vps_sigmoid(const float* src, float* dst, int64_t n, void* stream);
+/* gather rows: dst[i,:] = src[idx[i],:] for i < n (n from n_dev if given) */
+int vps_gather_rows(const float* src, const int32_t* idx, int n, const int* n_dev, int width, float* dst,
+                    void* stream);
+/* MaskROI pre-NMS (mask_roi.py:37-103 + bbox_transform.py:290-330 + clip_boxes :45-60): per (roi, class>=1):
+ * softmax prob, decode with weights (10,10,5,5), clip, class-agnostic fold; emits candidates with
+ * prob > score_thr: cand [m,5], cand_cls [m], m -> *ncand (order = (roi, class) ascending). */
+int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred, int nroi,
+                           const int* nroi_dev, int num_classes, float score_thr, float img_h, float img_w,
+                           float* cand, int32_t* cand_cls, float* cand_prob, int* ncand, void* stream);
+/* tracker score matrix (track_head.py:73-132, panoptic_fusetrack.py:412-424):
+ * comp[i,j] = log_softmax([0|X R^T])_ij + c0*log(p_i) + c1*[0|IoU]_ij + c2*[1|label eq]_ij ; then the
+ * sequential assignment loop (panoptic_fusetrack.py:428-469) on one thread. */
+int vps_track_assign(const float* emb, const float* ref_emb, int k, int m, int dim, const float* det_boxes,
+                     const float* ref_boxes, const int32_t* det_labels, const int32_t* ref_labels,
+                     const float* cls_prob, float c0, float c1, float c2, int32_t* det_obj_ids,
+                     int32_t* match_ids, float* comp_scores, void* stream);
+
+/* ---- panoptic fusion ------------------------------------------------------------------------- */
+/* MaskRemoval (mask_removal.py:29-92): boxes [k,4] f32, cls_prob[k], mask_logit [k,28,28] f32, cls_idx[k]
+ * (1-based). order = detections sorted by prob desc (stable).  Outputs keep flags in sorted order.
+ * occ: uint8 [num_things, H, W] workspace (zeroed by callee). */
+int vps_mask_removal(const float* boxes, const int32_t* order, int k, const float* mask_logit, int msize,
+                     const int32_t* cls_idx, int H, int W, float frac_thr, uint8_t* occ, int num_things,
+                     int32_t* keep_sorted, int* nkeep, void* stream);
+/* final fusion (unary_logits.py:81-108 SegTerm, mask_removal.py:86 paste, panoptic_fusetrack.py:588-593):
+ * per pixel argmax over [stuff(11) | inst_seg + mask_energy (k')] and semantic argmax over fcn_output,
+ * where fcn_output = bilinear x4 of fcn_score (upsnetFPN.py:59,80).  Nothing of size [k',H,W] is materialised.
+ * fcn_score NHWC f32 [1,h,w,19]; kept boxes [k',4], classes, mask logits [k',28,28]; outputs int64 [H,W]. */
+int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes, const int32_t* cls_idx,
+                      const float* mask_logit, int msize, int kkeep, int num_stuff, int H, int W,
+                      int64_t* pano_out, int64_t* sem_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPS_B200_H_ */

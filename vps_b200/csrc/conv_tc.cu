@@ -1,0 +1,521 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   M = 128 output pixels (a th x tw patch of one image), N = block_n output channels (<= 256),
+//   K = kh*kw*cin_pad consumed 64 channels (=128 B, one SWIZZLE_128B row) per pipeline stage.
+//
+//   warp 0  : TMA producer.  The A tile of one (r,s,channel-chunk) K-step is ONE 4-D TMA box
+//             {64 ch, tw, th, 1} of the NHWC activation tensor, shifted by the filter tap; the
+//             tensor map's element strides implement the conv stride and TMA's out-of-bounds zero
+//             fill implements the padding -- im2col is never materialised.  B tile = 2-D box of the
+//             packed weights [cout_pad][K].
+//   warp 1  : allocates TMEM (512 columns = two fp32 accumulators of up to 256 columns) and issues
+//             tcgen05.mma (M=128, N=block_n, K=16) x4 per stage from one elected lane; tcgen05.commit
+//             releases smem stages and publishes finished accumulators.
+//   warps 2-5: epilogue.  tcgen05.ld the accumulator (thread = output pixel, 32 channels per load),
+//             bias + activation + residual + scale, convert, vectorised NHWC store (also into a
+//             channel slice of a concat buffer / interleaved pixels for transposed convs).
+//   Persistent: grid = #SMs, static round-robin over tiles, double-buffered accumulators so the
+//   epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Replaces the cuDNN/cuBLAS calls behind every nn.Conv2d/ConvTranspose2d/Linear of the reference path.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 8;
+
+struct ConvTcParams {
+  int n_img, oh, ow;
+  int th, tw, tiles_y, tiles_x;
+  int n_tiles_n, block_n;
+  int kh, kw, sh, sw, ph, pw;
+  int cin_chunks;
+  int num_stages;
+  int total_tiles;
+  void* y;
+  int y_h, y_w, y_cs, y_dtype, y_vec;
+  int oy_mul, oy_off, ox_mul, ox_off;
+  const void* res;
+  int res_cs, res_dtype, res_after_act;
+  const float* bias;
+  int cout;
+  int act;
+  float slope, out_scale;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) {  // a lost arrival must fail loudly, never hang the GPU box
+      printf("vps conv_tc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (SWIZZLE_128B requirement)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.block_n * 128u;
+  const uint32_t bar_base = smem_base + (uint32_t)p.num_stages * stage_bytes;
+  // barrier slots (8 B each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int num_k = p.kh * p.kw * p.cin_chunks;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.n_tiles_n;
+        const int m_idx = tile / p.n_tiles_n;
+        const int img = m_idx / tiles_per_img;
+        const int rem = m_idx - img * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int x_base = tx * p.tw * p.sw - p.pw;
+        const int y_base = ty * p.th * p.sh - p.ph;
+        for (int r = 0; r < p.kh; ++r) {
+          for (int s = 0; s < p.kw; ++s) {
+            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+              mbar_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_4d(a_dst, &tmA, full_bar(stage), cc * BLOCK_K, x_base + s, y_base + r, img);
+              tma_load_2d(b_dst, &tmB, full_bar(stage), ((r * p.kw + s) * p.cin_chunks + cc) * BLOCK_K,
+                          n_idx * p.block_n);
+              if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kc = 0; kc < num_k; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      (uint32_t)((kc | k) != 0));
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int ty_in = row / p.tw, tx_in = row - ty_in * p.tw;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_idx = tile % p.n_tiles_n;
+      const int m_idx = tile / p.n_tiles_n;
+      const int img = m_idx / tiles_per_img;
+      const int rem = m_idx - img * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int oy = ty * p.th + ty_in, ox = tx * p.tw + tx_in;
+      const bool valid = (oy < p.oh) && (ox < p.ow);
+      const int64_t pix =
+          ((int64_t)img * p.y_h + (oy * p.oy_mul + p.oy_off)) * p.y_w + (ox * p.ox_mul + p.ox_off);
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        const int n0 = n_idx * p.block_n + c0;
+        if (valid && n0 < p.cout) {
+          const int nv = min(32, p.cout - n0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) v[j] += __ldg(p.bias + n0 + j);
+          }
+          float rs[32];
+          const bool has_res = p.res != nullptr;
+          if (has_res) {
+            const int64_t ro = pix * p.res_cs + n0;
+            if (p.res_dtype == VPS_BF16) {
+              const __nv_bfloat16* rp = (const __nv_bfloat16*)p.res + ro;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rs[j] = (j < nv) ? __bfloat162float(rp[j]) : 0.f;
+            } else {
+              const float* rp = (const float*)p.res + ro;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rs[j] = (j < nv) ? rp[j] : 0.f;
+            }
+            if (!p.res_after_act) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += rs[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = vps::apply_act(v[j], p.act, p.slope) * p.out_scale;
+          if (has_res && p.res_after_act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += rs[j];
+          }
+          const int64_t yo = pix * p.y_cs + n0;
+          if (p.y_dtype == VPS_BF16) {
+            __nv_bfloat16* yp = (__nv_bfloat16*)p.y + yo;
+            if (p.y_vec && nv == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *(uint32_t*)&b0; pk.y = *(uint32_t*)&b1; pk.z = *(uint32_t*)&b2; pk.w = *(uint32_t*)&b3;
+                *(uint4*)(yp + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) yp[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* yp = (float*)p.y + yo;
+            if (p.y_vec && nv == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *(float4*)(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) yp[j] = v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- weight packing
+// dst[co][ (r*kw+s)*cin_pad + ci ] (bf16), zero padded; src OIHW (or IOHW when transposed)
+__global__ void pack_weights_tc_kernel(const float* __restrict__ src, const float* __restrict__ scale,
+                                       __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh, int kw,
+                                       int cout_pad, int cin_pad, int transposed) {
+  const int64_t total = (int64_t)cout_pad * kh * kw * cin_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    int64_t t = i / cin_pad;
+    const int s = (int)(t % kw); t /= kw;
+    const int r = (int)(t % kh); t /= kh;
+    const int co = (int)t;
+    float v = 0.f;
+    if (co < cout && ci < cin) {
+      const int64_t si = transposed ? ((((int64_t)ci * cout + co) * kh + r) * kw + s)
+                                    : ((((int64_t)co * cin + ci) * kh + r) * kw + s);
+      v = src[si];
+      if (scale) v *= scale[co];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------- host
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+extern "C" int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw) {
+  const int64_t cout_pad = (cout + 15) / 16 * 16, cin_pad = (cin + 63) / 64 * 64;
+  return cout_pad * kh * kw * cin_pad * 2;
+}
+
+extern "C" int vps_pack_weights_tc(const float* w, const float* scale, void* dst, int cout, int cin, int kh,
+                                   int kw, int transposed, void* stream) {
+  const int cout_pad = (cout + 15) / 16 * 16, cin_pad = (cin + 63) / 64 * 64;
+  const int64_t total = (int64_t)cout_pad * kh * kw * cin_pad;
+  const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  pack_weights_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, scale, (__nv_bfloat16*)dst, cout, cin, kh,
+                                                                  kw, cout_pad, cin_pad, transposed);
+  VPS_CUDA_LAST("pack_weights_tc");
+  return VPS_OK;
+}
+
+extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) {
+  VPS_CHECK_ARG(a->x.dtype == VPS_BF16, "conv2d_tc: x must be bf16");
+  VPS_CHECK_ARG(a->x.cs % 8 == 0 && ((uintptr_t)a->x.ptr & 15) == 0, "conv2d_tc: x not 16B aligned (cs=%d)",
+                a->x.cs);
+  VPS_CHECK_ARG(a->sh >= 1 && a->sh <= 2 && a->sw >= 1 && a->sw <= 2, "conv2d_tc: stride must be 1 or 2");
+  VPS_CHECK_ARG(a->cin == a->x.c, "conv2d_tc: cin %d != x.c %d", a->cin, a->x.c);
+  VPS_CHECK_ARG(((uintptr_t)a->w & 15) == 0, "conv2d_tc: weights not aligned");
+  auto encode = get_encode();
+  if (!encode) { vps::set_error("cuTensorMapEncodeTiled unavailable"); return VPS_E_CUDA; }
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) { vps::set_error("no device"); return VPS_E_NODEV; }
+  }
+
+  ConvTcParams p;
+  const int cin_pad = (a->cin + 63) / 64 * 64;
+  const int cout_pad = (a->cout + 15) / 16 * 16;
+  p.n_img = a->x.n; p.oh = a->oh; p.ow = a->ow;
+  // pixel patch: minimise padded area; th*tw == 128, box extent tw*sw <= 256
+  int best_tw = 16; int64_t best_area = -1;
+  const int cands[5] = {16, 8, 32, 64, 128};
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cands[i], th = 128 / tw;
+    if (tw * a->sw > 256 || th * a->sh > 256) continue;
+    const int64_t area = (int64_t)vps::cdiv(a->ow, tw) * tw * vps::cdiv(a->oh, th) * th;
+    if (best_area < 0 || area < best_area) { best_area = area; best_tw = tw; }
+  }
+  p.tw = best_tw; p.th = 128 / best_tw;
+  p.tiles_x = vps::cdiv(a->ow, p.tw); p.tiles_y = vps::cdiv(a->oh, p.th);
+  // N tile: whole cout_pad if <= 256, else the largest multiple of 16 <= 256 dividing it
+  int block_n = cout_pad;
+  if (block_n > 256) {
+    block_n = 256;
+    while (cout_pad % block_n) block_n -= 16;
+  }
+  p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
+  p.kh = a->kh; p.kw = a->kw; p.sh = a->sh; p.sw = a->sw; p.ph = a->ph; p.pw = a->pw;
+  p.cin_chunks = cin_pad / 64;
+  const int stage_bytes = A_STAGE_BYTES + block_n * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  p.num_stages = stages;
+  p.total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  p.y = a->y.ptr; p.y_h = a->y.h; p.y_w = a->y.w; p.y_cs = a->y.cs; p.y_dtype = a->y.dtype;
+  const int esz = a->y.dtype == VPS_BF16 ? 2 : 4;
+  p.y_vec = (((uintptr_t)a->y.ptr & 15) == 0) && ((a->y.cs * esz) % 16 == 0);
+  p.oy_mul = a->oy_mul; p.oy_off = a->oy_off; p.ox_mul = a->ox_mul; p.ox_off = a->ox_off;
+  p.res = a->res.ptr; p.res_cs = a->res.cs; p.res_dtype = a->res.dtype; p.res_after_act = a->res_after_act;
+  p.bias = a->bias; p.cout = a->cout; p.act = a->act; p.slope = a->slope; p.out_scale = a->out_scale;
+  VPS_CHECK_ARG((a->oh - 1) * a->oy_mul + a->oy_off < a->y.h && (a->ow - 1) * a->ox_mul + a->ox_off < a->y.w,
+                "conv2d_tc: output mapping out of range");
+  if (a->res.ptr) VPS_CHECK_ARG(a->res.h == a->y.h && a->res.w == a->y.w, "conv2d_tc: residual geometry");
+  if (p.total_tiles == 0) return VPS_OK;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->x.c, (cuuint64_t)a->x.w, (cuuint64_t)a->x.h, (cuuint64_t)a->x.n};
+    cuuint64_t strides[3] = {(cuuint64_t)a->x.cs * 2, (cuuint64_t)a->x.w * a->x.cs * 2,
+                             (cuuint64_t)a->x.h * a->x.w * a->x.cs * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.tw * a->sw), (cuuint32_t)(p.th * a->sh), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)a->sw, (cuuint32_t)a->sh, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vps::set_error("conv2d_tc: encode A failed (%d) dims %d,%d,%d,%d cs %d box %d,%d", (int)r, a->x.c,
+                     a->x.w, a->x.h, a->x.n, a->x.cs, p.tw * a->sw, p.th * a->sh);
+      return VPS_E_CUDA;
+    }
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)a->kh * a->kw * cin_pad;
+    cuuint64_t dims[2] = {K, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
+  }
+  const int smem = stages * stage_bytes + 1024 + 8 * (2 * MAX_STAGES + 8);
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    if (cudaFuncSetAttribute(conv_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess) {
+      vps::set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(cudaGetLastError()));
+      return VPS_E_CUDA;
+    }
+    smem_set = 227 * 1024;
+  }
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  conv_igemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  VPS_CUDA_LAST("conv_igemm_tc_kernel");
+  return VPS_OK;
+}

@@ -1,0 +1,220 @@
+// FlowNet2 native ops: correlation, resample2d, channelnorm (NHWC, f32 or bf16 storage, fp32 math).
+// Semantics follow correlation_cuda_kernel.cu:74-147, resample2d_kernel.cu:16-71,
+// channelnorm_kernel.cu:19-60 of the reference (see include/vps_b200.h).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ correlation (CUDA-core version)
+// Block = one output row segment of 32 pixels; lane = pixel, warp w owns displacement rows
+// tj = w, w+8, w+16 and all D column displacements.  Channel chunks of CK are staged in shared memory
+// channel-major so lanes read consecutive words (no bank conflicts); the reference's separate
+// NCHW->padded-NHWC repack pass (correlation_cuda_kernel.cu:47-70) does not exist here: zero padding
+// is applied while staging.
+constexpr int CK = 16;
+
+template <typename T, int D, int S2>
+__global__ void __launch_bounds__(256) correlation_kernel(vps::TV<const T> f1, vps::TV<const T> f2,
+                                                          vps::TV<T> out, int act, float slope) {
+  constexpr int R = (D - 1) / 2;
+  constexpr int PW = 32 + (D - 1) * S2;
+  constexpr int JT = (D + 7) / 8;
+  extern __shared__ float sm[];
+  float* f1s = sm;                 // [CK][32]
+  float* f2s = sm + CK * 32;       // [CK][D][PW]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y = blockIdx.y, n = blockIdx.z;
+  const int H = f1.h, W = f1.w, C = f1.c;
+  float acc[JT][D];
+#pragma unroll
+  for (int a = 0; a < JT; ++a)
+#pragma unroll
+    for (int b = 0; b < D; ++b) acc[a][b] = 0.f;
+
+  for (int c0 = 0; c0 < C; c0 += CK) {
+    // stage f1: 32 px x CK ch
+    for (int i = threadIdx.x; i < 32 * CK; i += 256) {
+      const int c = i % CK, px = i / CK;
+      const int x = x0 + px;
+      float v = 0.f;
+      if (x < W && c0 + c < C) v = vps::ldf<T>(f1.p + f1.off(n, y, x) + c0 + c);
+      f1s[c * 32 + px] = v;
+    }
+    // stage f2: D rows x PW px x CK ch
+    for (int i = threadIdx.x; i < D * PW * CK; i += 256) {
+      const int c = i % CK;
+      const int t = i / CK;
+      const int px = t % PW, row = t / PW;
+      const int x = x0 + px - R * S2, yy = y + (row - R) * S2;
+      float v = 0.f;
+      if (x >= 0 && x < W && yy >= 0 && yy < H && c0 + c < C) v = vps::ldf<T>(f2.p + f2.off(n, yy, x) + c0 + c);
+      f2s[(c * D + row) * PW + px] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < CK; ++c) {
+      const float a = f1s[c * 32 + lane];
+#pragma unroll
+      for (int jt = 0; jt < JT; ++jt) {
+        const int tj = w + 8 * jt;
+        if (tj < D) {
+          const float* rowp = f2s + (c * D + tj) * PW + lane;
+#pragma unroll
+          for (int ti = 0; ti < D; ++ti) acc[jt][ti] = fmaf(a, rowp[ti * S2], acc[jt][ti]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int x = x0 + lane;
+  if (x < W) {
+    const float inv = 1.f / (float)C;
+    T* op = out.p + out.off(n, y, x);
+#pragma unroll
+    for (int jt = 0; jt < JT; ++jt) {
+      const int tj = w + 8 * jt;
+      if (tj < D) {
+#pragma unroll
+        for (int ti = 0; ti < D; ++ti) {
+          float v = acc[jt][ti] * inv;
+          v = vps::apply_act(v, act, slope);
+          vps::stf<T>(op + tj * D + ti, v);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int D, int S2>
+int launch_corr(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int act, float slope,
+                cudaStream_t st) {
+  constexpr int PW = 32 + (D - 1) * S2;
+  const int smem = (CK * 32 + CK * D * PW) * 4;
+  auto kern = correlation_kernel<T, D, S2>;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      vps::set_error("correlation: smem attr: %s", cudaGetErrorString(cudaGetLastError()));
+      return VPS_E_CUDA;
+    }
+  }
+  dim3 grid(vps::cdiv(f1->w, 32), f1->h, f1->n);
+  kern<<<grid, 256, smem, st>>>(vps::tv<const T>(*f1), vps::tv<const T>(*f2), vps::tv<T>(*out), act, slope);
+  VPS_CUDA_LAST("correlation_kernel");
+  return VPS_OK;
+}
+
+// ------------------------------------------------------------------ resample2d
+template <typename T, typename TF>
+__global__ void resample2d_kernel(vps::TV<const T> src, vps::TV<const TF> flow, vps::TV<T> out, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % out.c);
+    int64_t t = i / out.c;
+    const int x = (int)(t % out.w); t /= out.w;
+    const int y = (int)(t % out.h);
+    const int n = (int)(t / out.h);
+    const TF* fp = flow.p + flow.off(n, y, x);
+    const float dx = vps::ldf<TF>(fp), dy = vps::ldf<TF>(fp + 1);
+    const float xf = (float)x + dx, yf = (float)y + dy;
+    const float alpha = xf - floorf(xf), beta = yf - floorf(yf);
+    // border clamp of the tap coordinates, fractional weights NOT renormalised (resample2d_kernel.cu:44-52)
+    const int xL = max(min((int)floorf(xf), src.w - 1), 0);
+    const int xR = max(min((int)floorf(xf) + 1, src.w - 1), 0);
+    const int yT = max(min((int)floorf(yf), src.h - 1), 0);
+    const int yB = max(min((int)floorf(yf) + 1, src.h - 1), 0);
+    float v = 0.f;
+    v += (1.f - alpha) * (1.f - beta) * vps::ldf<T>(src.p + src.off(n, yT, xL) + c);
+    v += (alpha) * (1.f - beta) * vps::ldf<T>(src.p + src.off(n, yT, xR) + c);
+    v += (1.f - alpha) * (beta) * vps::ldf<T>(src.p + src.off(n, yB, xL) + c);
+    v += (alpha) * (beta) * vps::ldf<T>(src.p + src.off(n, yB, xR) + c);
+    vps::stf<T>(out.p + out.off(n, y, x) + c, v);
+  }
+}
+
+// ------------------------------------------------------------------ channelnorm
+template <typename T, typename TO>
+__global__ void channelnorm_kernel(vps::TV<const T> a, vps::TV<const T> b, int has_b, vps::TV<TO> out,
+                                   int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % a.w);
+    int64_t t = i / a.w;
+    const int y = (int)(t % a.h);
+    const int n = (int)(t / a.h);
+    const T* ap = a.p + a.off(n, y, x);
+    const T* bp = has_b ? b.p + b.off(n, y, x) : nullptr;
+    float s = 0.f;
+    for (int c = 0; c < a.c; ++c) {
+      float v = vps::ldf<T>(ap + c);
+      if (has_b) v -= vps::ldf<T>(bp + c);
+      s += v * v;
+    }
+    vps::stf<TO>(out.p + out.off(n, y, x), sqrtf(s));
+  }
+}
+
+inline int grid_for(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+extern "C" int vps_correlation(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
+                               int max_disp, int stride1, int stride2, int act, float slope, void* stream) {
+  VPS_CHECK_ARG(stride1 == 1 && pad == max_disp, "correlation: only stride1=1, pad==max_displacement");
+  VPS_CHECK_ARG(f1->dtype == f2->dtype && f1->dtype == out->dtype, "correlation: dtype mismatch");
+  VPS_CHECK_ARG(f1->h == f2->h && f1->w == f2->w && f1->c == f2->c && out->h == f1->h && out->w == f1->w,
+                "correlation: shape mismatch");
+  const int R = max_disp / stride2, D = 2 * R + 1;
+  VPS_CHECK_ARG(out->c == D * D, "correlation: out.c %d != %d", out->c, D * D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 21 && stride2 == 2) {
+    VPS_DISPATCH_T(f1->dtype, T, return (launch_corr<T, 21, 2>(f1, f2, out, act, slope, st)));
+  } else if (D == 9 && stride2 == 1) {
+    VPS_DISPATCH_T(f1->dtype, T, return (launch_corr<T, 9, 1>(f1, f2, out, act, slope, st)));
+  }
+  vps::set_error("correlation: unsupported (max_disp %d, stride2 %d)", max_disp, stride2);
+  return VPS_E_ARG;
+}
+
+extern "C" int vps_resample2d(const vps_tensor* src, const vps_tensor* flow, const vps_tensor* out, void* stream) {
+  VPS_CHECK_ARG(src->dtype == out->dtype && src->c == out->c && flow->c >= 2, "resample2d: bad args");
+  VPS_CHECK_ARG(flow->h == out->h && flow->w == out->w, "resample2d: flow/out size");
+  const int64_t total = (int64_t)out->n * out->h * out->w * out->c;
+  if (!total) return VPS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(total, 256);
+  VPS_DISPATCH_T(src->dtype, T, {
+    if (flow->dtype == VPS_F32)
+      resample2d_kernel<T, float><<<g, 256, 0, st>>>(vps::tv<const T>(*src), vps::tv<const float>(*flow),
+                                                    vps::tv<T>(*out), total);
+    else
+      resample2d_kernel<T, __nv_bfloat16><<<g, 256, 0, st>>>(vps::tv<const T>(*src),
+                                                            vps::tv<const __nv_bfloat16>(*flow),
+                                                            vps::tv<T>(*out), total);
+  });
+  VPS_CUDA_LAST("resample2d_kernel");
+  return VPS_OK;
+}
+
+extern "C" int vps_channelnorm(const vps_tensor* a, const vps_tensor* b, const vps_tensor* out, void* stream) {
+  VPS_CHECK_ARG(out->c == 1 && out->h == a->h && out->w == a->w, "channelnorm: out shape");
+  if (b) VPS_CHECK_ARG(b->dtype == a->dtype && b->c == a->c && b->h == a->h && b->w == a->w, "channelnorm: b");
+  const int64_t total = (int64_t)a->n * a->h * a->w;
+  if (!total) return VPS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(total, 256);
+  vps_tensor bb = b ? *b : *a;
+  VPS_DISPATCH_T(a->dtype, T, {
+    if (out->dtype == VPS_F32)
+      channelnorm_kernel<T, float><<<g, 256, 0, st>>>(vps::tv<const T>(*a), vps::tv<const T>(bb), b != nullptr,
+                                                     vps::tv<float>(*out), total);
+    else
+      channelnorm_kernel<T, __nv_bfloat16><<<g, 256, 0, st>>>(vps::tv<const T>(*a), vps::tv<const T>(bb),
+                                                             b != nullptr, vps::tv<__nv_bfloat16>(*out), total);
+  });
+  VPS_CUDA_LAST("channelnorm_kernel");
+  return VPS_OK;
+}
