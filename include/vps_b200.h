@@ -153,56 +153,73 @@ int vps_deform_im2col(const vps_tensor* x, const vps_tensor* offset, const vps_t
 
 /* ---- detection ops --------------------------------------------------------------------------- */
 /* RoIAlign legacy mmdet v1 (roi_align_kernel.cu:16-128) with FPN level mapping
- * (single_level.py:54-73, finest_scale 56).  feats: nlev NHWC maps, strides[nlev]; rois device
- * f32 [nroi,5]; out NHWC [nroi, ps, ps, c].  nroi_dev (may be NULL) = device int holding the valid count. */
+ * (single_level.py:54-73, finest_scale 56), all levels in one launch.  feats: nlev NHWC maps,
+ * strides[nlev]; rois device f32 [nroi,5] (batch,x1,y1,x2,y2); out NHWC [>=nroi, ps, ps, c]
+ * (flattened (ph,pw,c): the FC weights are permuted to this order at pack time).
+ * nroi_dev (may be NULL) = device int holding the valid count; rows beyond it are zero-filled. */
 int vps_roi_align(const vps_tensor* feats, const int* strides, int nlev, const float* rois, int nroi,
                   const int* nroi_dev, const vps_tensor* out, int sample_num, void* stream);
-/* stable descending sort of keys with payload indices; n <= 2^20 (segmented: nseg segments of
- * length seglen).  Outputs sorted keys + original indices; top-k = prefix. */
+/* stable descending radix sort of float keys with their original indices (ties keep ascending index:
+ * the pinned version of the reference's unspecified topk / argsort tie order).
+ * ws must hold at least n*4 + 256 + cub temp bytes (n*24 + 64 KiB is always enough). */
 int vps_sort_desc(const float* keys, float* keys_out, int32_t* idx_out, int n, void* ws, int64_t ws_bytes,
                   void* stream);
-/* RPN per-level candidate decode (rpn_head.py:66-85 + delta2bbox transforms.py:34-68):
- * for the top `k` sorted indices: anchor from index, decode, clamp; writes dets [k,5] (x1,y1,x2,y2,score). */
+/* RPN objectness (rpn_head.py:69-72): sigmoid of an NHWC score map, flattened in the reference's
+ * (h, w, anchor) order into dst[h*w*c]. */
+int vps_sigmoid_flat(const vps_tensor* src, float* dst, void* stream);
+/* RPN per-level candidate decode (rpn_head.py:73-85 + delta2bbox transforms.py:34-68, means 0 stds 1):
+ * for the top k sorted flat indices: anchor from index, decode, clamp to the image;
+ * dets [k,5] = (x1,y1,x2,y2,score) in score order. */
 int vps_rpn_decode(const float* scores_sorted, const int32_t* idx_sorted, int k, const vps_tensor* deltas,
                    int feat_h, int feat_w, int stride, const float* base_anchors, int num_anchors,
                    float img_h, float img_w, float* dets, void* stream);
-/* greedy NMS (nms_kernel.cu:13-131): dets [n,5] sorted by score desc; IoU with +1 extents, suppress when
- * IoU > thr.  Entirely on device: keep_idx[0..*nkeep) ascending (== score order).  n may be read from n_dev. */
+/* greedy NMS (nms_kernel.cu:13-131 / upsnet nms_kernel.cu:40-150): dets [n,5] already sorted by score
+ * (descending); IoU with +1 extents, suppress when IoU > thr.  Bitmask kernel + the reference's host
+ * greedy loop run as a single-block device pass: no D2H.  keep_idx[0..*nkeep) = kept positions,
+ * ascending (= score order).  If n_dev != NULL the valid count is read from it (<= n).
+ * ws >= n * ceil(n/64) * 8 bytes. */
 int vps_nms(const float* dets, int n, const int* n_dev, float thr, int32_t* keep_idx, int* nkeep,
             void* ws, int64_t ws_bytes, void* stream);
-/* sigmoid on a flat NHWC map flattened to the reference's (h, w, a) order is the identity layout. */
-int vps_sigmoid(const float* src, float* dst, int64_t n, void* stream);
-/* gather rows: dst[i,:] = src[idx[i],:] for i < n (n from n_dev if given) */
+/* dst[i,:] = src[idx[i],:] for i < n (valid count from n_dev if given; rows beyond are zeroed) */
 int vps_gather_rows(const float* src, const int32_t* idx, int n, const int* n_dev, int width, float* dst,
                     void* stream);
-/* MaskROI pre-NMS (mask_roi.py:37-103 + bbox_transform.py:290-330 + clip_boxes :45-60): per (roi, class>=1):
- * softmax prob, decode with weights (10,10,5,5), clip, class-agnostic fold; emits candidates with
- * prob > score_thr: cand [m,5], cand_cls [m], m -> *ncand (order = (roi, class) ascending). */
+/* MaskROI pre-NMS (mask_roi.py:37-93 + upsnet bbox_transform.py:290-330 weights (10,10,5,5) +
+ * clip_boxes :45-60): slot (roi*8 + class-1) of cand [nroi*8,5] gets the decoded, clipped box and
+ * softmax prob if prob > score_thr, else prob = -1 (class-agnostic fold order, deterministic);
+ * *ncand = number of valid slots. */
 int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred, int nroi,
                            const int* nroi_dev, int num_classes, float score_thr, float img_h, float img_w,
                            float* cand, int32_t* cand_cls, float* cand_prob, int* ncand, void* stream);
-/* tracker score matrix (track_head.py:73-132, panoptic_fusetrack.py:412-424):
- * comp[i,j] = log_softmax([0|X R^T])_ij + c0*log(p_i) + c1*[0|IoU]_ij + c2*[1|label eq]_ij ; then the
- * sequential assignment loop (panoptic_fusetrack.py:428-469) on one thread. */
+/* tracker (track_head.py:73-132, panoptic_fusetrack.py:412-469): dots = emb . ref_emb^T,
+ * comp = log_softmax([0|dots]) + c0*log(p) + c1*[0|IoU] + c2*[1|label eq], row argmax (first max),
+ * then the sequential id-assignment loop on one device thread.  Outputs det_obj_ids[k], match_ids[k],
+ * comp_scores [k,m+1], mem_src[cap] (detection whose RoI features/box end in memory slot j, -1 =
+ * unchanged) and *new_m.  ws >= (k*m + k + 2*cap)*4 bytes. */
 int vps_track_assign(const float* emb, const float* ref_emb, int k, int m, int dim, const float* det_boxes,
                      const float* ref_boxes, const int32_t* det_labels, const int32_t* ref_labels,
-                     const float* cls_prob, float c0, float c1, float c2, int32_t* det_obj_ids,
-                     int32_t* match_ids, float* comp_scores, void* stream);
+                     const float* cls_prob, float c0, float c1, float c2, int cap, int32_t* det_obj_ids,
+                     int32_t* match_ids, float* comp_scores, int32_t* mem_src, int* new_m, void* ws,
+                     int64_t ws_bytes, void* stream);
 
 /* ---- panoptic fusion ------------------------------------------------------------------------- */
-/* MaskRemoval (mask_removal.py:29-92): boxes [k,4] f32, cls_prob[k], mask_logit [k,28,28] f32, cls_idx[k]
- * (1-based). order = detections sorted by prob desc (stable).  Outputs keep flags in sorted order.
- * occ: uint8 [num_things, H, W] workspace (zeroed by callee). */
-int vps_mask_removal(const float* boxes, const int32_t* order, int k, const float* mask_logit, int msize,
-                     const int32_t* cls_idx, int H, int W, float frac_thr, uint8_t* occ, int num_things,
+/* MaskRemoval (mask_removal.py:29-92): boxes [k,4] f32, mask_logit [k,ms,ms] f32, cls_idx[k] (1-based),
+ * order[k] = detection indices sorted by prob (descending, stable).  cv2.resize(INTER_LINEAR) of each
+ * 28x28 logit map is evaluated on the fly; occ = uint8 [num_things,H,W] class occupancy workspace.
+ * Outputs keep_flag[k] (sorted order), keep_sorted[0..*nkeep) = kept detection indices in sorted order.
+ * counters: uint32 [2k] workspace. */
+int vps_mask_removal(const float* boxes, const int32_t* order, int k, const int* k_dev,
+                     const float* mask_logit, int msize, const int32_t* cls_idx, int H, int W, float frac_thr,
+                     uint8_t* occ, int num_things, unsigned int* counters, int32_t* keep_flag,
                      int32_t* keep_sorted, int* nkeep, void* stream);
-/* final fusion (unary_logits.py:81-108 SegTerm, mask_removal.py:86 paste, panoptic_fusetrack.py:588-593):
- * per pixel argmax over [stuff(11) | inst_seg + mask_energy (k')] and semantic argmax over fcn_output,
- * where fcn_output = bilinear x4 of fcn_score (upsnetFPN.py:59,80).  Nothing of size [k',H,W] is materialised.
- * fcn_score NHWC f32 [1,h,w,19]; kept boxes [k',4], classes, mask logits [k',28,28]; outputs int64 [H,W]. */
+/* final fusion (SegTerm unary_logits.py:81-108, paste mask_removal.py:86, argmax
+ * panoptic_fusetrack.py:588-593): per full-resolution pixel, fcn_output = bilinear x4 of fcn_score
+ * (upsnetFPN.py:59,80) computed in registers; pano_out = argmax over [stuff(num_stuff) | kept
+ * instances (seg term + pasted mask logit)], sem_out = argmax over all classes; int64 [H,W] each.
+ * dummy != 0: the MaskROI "no detection" result (one all-zero instance channel). */
 int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes, const int32_t* cls_idx,
-                      const float* mask_logit, int msize, int kkeep, int num_stuff, int H, int W,
-                      int64_t* pano_out, int64_t* sem_out, void* stream);
+                      const float* mask_logit, int msize, const int32_t* keep_sorted, const int* nkeep_dev,
+                      int kcap, int num_stuff, int dummy, int H, int W, int64_t* pano_out, int64_t* sem_out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _nhwc(t, dtype):
-    return t.permute(0, 2, 3, 1).contiguous().to(dtype)
+    """NCHW cpu tensor -> NHWC view whose pixel stride is padded to a multiple of 8 (TMA alignment)."""
+    n, c, h, w = t.shape
+    cs = (c + 7) // 8 * 8
+    buf = torch.zeros(n, h, w, cs, dtype=dtype)
+    buf[..., :c] = t.permute(0, 2, 3, 1).to(dtype)
+    return buf
 
 
 CASES = [
@@ -38,7 +43,7 @@ def test_conv_tc_vs_oracle(cuda, case):
     xq, wq = x.bfloat16().float(), wt.bfloat16().float()
     ref = F.leaky_relu(F.conv2d(xq, wq, b, stride=s, padding=p), 0.1)
     pk = ops.PackedConv(wt.to(cuda), b.to(cuda))
-    xd = _nhwc(x, torch.bfloat16).to(cuda)
+    xd = _nhwc(x, torch.bfloat16).to(cuda)[..., :cin]
     oh, ow = ref.shape[2:]
     y = torch.full((n, oh, ow, cout), float("nan"), dtype=torch.float32, device=cuda)
     ops.conv2d(xd, pk, y, stride=s, pad=p, act=ops.ACT_LRELU, slope=0.1)
@@ -59,7 +64,7 @@ def test_conv_simt_vs_oracle(cuda, case):
     res = torch.randn(n, cout, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1, generator=g)
     ref = F.relu(F.conv2d(x, wt, b, stride=s, padding=p) + res)
     pk = ops.PackedConv(wt.to(cuda), b.to(cuda))
-    xd = _nhwc(x, torch.float32).to(cuda)
+    xd = _nhwc(x, torch.float32).to(cuda)[..., :cin]
     rd = _nhwc(res, torch.float32).to(cuda)
     y = torch.empty_like(rd)
     ops.conv2d(xd, pk, y, stride=s, pad=p, act=ops.ACT_RELU, res=rd)

@@ -66,7 +66,7 @@ EXPORTS = [
     "vps_resize_bilinear", "vps_resize_nearest", "vps_pool2d", "vps_groupnorm",
     "vps_bfp_gather", "vps_bfp_scatter", "vps_flow_warp", "vps_tcea_temporal", "vps_tcea_combine",
     "vps_deform_im2col",
-    "vps_roi_align", "vps_sort_desc", "vps_rpn_decode", "vps_nms", "vps_sigmoid", "vps_gather_rows",
+    "vps_roi_align", "vps_sort_desc", "vps_rpn_decode", "vps_nms", "vps_sigmoid_flat", "vps_gather_rows",
     "vps_maskroi_candidates", "vps_track_assign",
     "vps_mask_removal", "vps_panoptic_fuse",
 ]

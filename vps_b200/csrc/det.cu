@@ -1,0 +1,440 @@
+// Detection-side kernels: RoIAlign with FPN level mapping, stable descending sort (CUB radix sort),
+// RPN decode, greedy NMS entirely on device, MaskROI candidate generation, tracker assignment.
+// All index-producing kernels are deterministic (no atomics in ordering decisions).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+inline int grid_for(int64_t total, int threads = 256) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+#define GRID_STRIDE(i, total) \
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (total); i += (int64_t)gridDim.x * blockDim.x)
+
+// ------------------------------------------------------------------ RoIAlign
+constexpr int MAXLEV = 4;
+template <typename T>
+struct Feats {
+  vps::TV<const T> l[MAXLEV];
+  float scale[MAXLEV];
+  int n;
+};
+
+// roi_align_kernel.cu:16-45
+template <typename T>
+__device__ __forceinline__ float bilinear_legacy(const vps::TV<const T>& f, int b, int c, float y, float x) {
+  const int H = f.h, W = f.w;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) return 0.f;
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int y_low = (int)y, x_low = (int)x, y_high, x_high;
+  if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else { y_high = y_low + 1; }
+  if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else { x_high = x_low + 1; }
+  const float ly = y - (float)y_low, lx = x - (float)x_low;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float lt = vps::ldf<T>(f.p + f.off(b, y_low, x_low) + c);
+  const float rt = vps::ldf<T>(f.p + f.off(b, y_low, x_high) + c);
+  const float lb = vps::ldf<T>(f.p + f.off(b, y_high, x_low) + c);
+  const float rb = vps::ldf<T>(f.p + f.off(b, y_high, x_high) + c);
+  const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+  return w1 * lt + w2 * rt + w3 * lb + w4 * rb;
+}
+
+// ROIAlignForward (roi_align_kernel.cu:64-128) + map_roi_levels (single_level.py:54-73), one launch for all levels.
+template <typename T>
+__global__ void roi_align_kernel(Feats<T> fs, const float* __restrict__ rois, int nroi, const int* __restrict__ nroi_dev,
+                                 vps::TV<T> out, int ps, int sample_num, int64_t total) {
+  const int nvalid = nroi_dev ? min(*nroi_dev, nroi) : nroi;
+  const int C = out.c;
+  GRID_STRIDE(i, total) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int pw = (int)(t % ps); t /= ps;
+    const int ph = (int)(t % ps);
+    const int r = (int)(t / ps);
+    T* op = out.p + out.off(r, ph, pw) + c;
+    if (r >= nvalid) { vps::stf<T>(op, 0.f); continue; }
+    const float* roi = rois + (int64_t)r * 5;
+    const int b = (int)roi[0];
+    const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
+    const float sc = sqrtf((x2 - x1 + 1.f) * (y2 - y1 + 1.f));
+    int lvl = (int)floorf(log2f(sc / 56.f + 1e-6f));
+    lvl = max(0, min(lvl, fs.n - 1));
+    const float ss = fs.scale[lvl];
+    const float rsw = x1 * ss, rsh = y1 * ss, rew = (x2 + 1.f) * ss, reh = (y2 + 1.f) * ss;
+    const float rw = fmaxf(rew - rsw, 0.f), rh = fmaxf(reh - rsh, 0.f);
+    const float bh = rh / (float)ps, bw = rw / (float)ps;
+    float acc = 0.f;
+    for (int iy = 0; iy < sample_num; ++iy) {
+      const float y = rsh + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)sample_num;
+      for (int ix = 0; ix < sample_num; ++ix) {
+        const float x = rsw + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)sample_num;
+        acc += bilinear_legacy<T>(fs.l[lvl], b, c, y, x);
+      }
+    }
+    vps::stf<T>(op, acc / (float)(sample_num * sample_num));
+  }
+}
+
+// ------------------------------------------------------------------ RPN decode (rpn_head.py:73-85, transforms.py:34-68)
+template <typename T>
+__global__ void rpn_decode_kernel(const float* __restrict__ scores_sorted, const int32_t* __restrict__ idx_sorted, int k,
+                                  vps::TV<const T> deltas, int feat_w, int stride, const float* __restrict__ base,
+                                  int A, float img_h, float img_w, float* __restrict__ dets) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const int idx = idx_sorted[i];
+  const int a = idx % A, pix = idx / A;
+  const int x = pix % feat_w, y = pix / feat_w;
+  const float ax1 = base[a * 4 + 0] + (float)(x * stride), ay1 = base[a * 4 + 1] + (float)(y * stride);
+  const float ax2 = base[a * 4 + 2] + (float)(x * stride), ay2 = base[a * 4 + 3] + (float)(y * stride);
+  const T* dp = deltas.p + deltas.off(0, y, x) + a * 4;
+  const float dx = vps::ldf<T>(dp), dy = vps::ldf<T>(dp + 1);
+  float dw = vps::ldf<T>(dp + 2), dh = vps::ldf<T>(dp + 3);
+  const float max_ratio = 4.135166556742356f;  // |log(16/1000)|
+  dw = fminf(fmaxf(dw, -max_ratio), max_ratio);
+  dh = fminf(fmaxf(dh, -max_ratio), max_ratio);
+  const float px = (ax1 + ax2) * 0.5f, py = (ay1 + ay2) * 0.5f;
+  const float pw = ax2 - ax1 + 1.0f, ph = ay2 - ay1 + 1.0f;
+  const float gw = pw * expf(dw), gh = ph * expf(dh);
+  const float gx = px + pw * dx, gy = py + ph * dy;
+  float bx1 = gx - gw * 0.5f + 0.5f, by1 = gy - gh * 0.5f + 0.5f;
+  float bx2 = gx + gw * 0.5f - 0.5f, by2 = gy + gh * 0.5f - 0.5f;
+  bx1 = fminf(fmaxf(bx1, 0.f), img_w - 1.f);
+  by1 = fminf(fmaxf(by1, 0.f), img_h - 1.f);
+  bx2 = fminf(fmaxf(bx2, 0.f), img_w - 1.f);
+  by2 = fminf(fmaxf(by2, 0.f), img_h - 1.f);
+  float* o = dets + (int64_t)i * 5;
+  o[0] = bx1; o[1] = by1; o[2] = bx2; o[3] = by2; o[4] = scores_sorted[i];
+}
+
+// ------------------------------------------------------------------ NMS (nms_kernel.cu:13-131)
+__device__ __forceinline__ float dev_iou(const float* a, const float* b) {
+  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  const float width = fmaxf(right - left + 1.f, 0.f), height = fmaxf(bottom - top + 1.f, 0.f);
+  const float inter = width * height;
+  const float sa = (a[2] - a[0] + 1.f) * (a[3] - a[1] + 1.f);
+  const float sb = (b[2] - b[0] + 1.f) * (b[3] - b[1] + 1.f);
+  return inter / (sa + sb - inter);
+}
+
+__global__ void nms_mask_kernel(int n_cap, const int* __restrict__ n_dev, float thr, const float* __restrict__ boxes,
+                                unsigned long long* __restrict__ mask, int col_blocks) {
+  const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  const int row_start = blockIdx.y, col_start = blockIdx.x;
+  if (row_start * 64 >= n || col_start * 64 >= n) return;
+  const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
+  __shared__ float bb[64 * 5];
+  if (threadIdx.x < col_size) {
+    for (int j = 0; j < 5; ++j) bb[threadIdx.x * 5 + j] = boxes[(int64_t)(64 * col_start + threadIdx.x) * 5 + j];
+  }
+  __syncthreads();
+  if (threadIdx.x < row_size) {
+    const int cur = 64 * row_start + threadIdx.x;
+    const float* cb = boxes + (int64_t)cur * 5;
+    unsigned long long t = 0;
+    const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+    for (int i = start; i < col_size; ++i)
+      if (dev_iou(cb, bb + i * 5) > thr) t |= 1ULL << i;
+    mask[(int64_t)cur * col_blocks + col_start] = t;
+  }
+}
+
+// The host greedy loop of the reference (nms_kernel.cu:104-123) as a single-block device pass: no D2H.
+__global__ void nms_reduce_kernel(int n_cap, const int* __restrict__ n_dev, const unsigned long long* __restrict__ mask,
+                                  int col_blocks, int32_t* __restrict__ keep, int* __restrict__ nkeep) {
+  extern __shared__ unsigned long long remv[];
+  const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  const int cb = (n + 63) / 64;
+  for (int j = threadIdx.x; j < cb; j += blockDim.x) remv[j] = 0ULL;
+  __shared__ int s_num;
+  if (threadIdx.x == 0) s_num = 0;
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const int nb = i >> 6, ib = i & 63;
+    const bool kept = !(remv[nb] & (1ULL << ib));   // all threads read the same word
+    __syncthreads();
+    if (kept) {
+      if (threadIdx.x == 0) keep[s_num++] = i;
+      const unsigned long long* p = mask + (int64_t)i * col_blocks;
+      for (int j = nb + threadIdx.x; j < cb; j += blockDim.x) remv[j] |= p[j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *nkeep = s_num;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n_cap,
+                                   const int* __restrict__ n_dev, int width, float* __restrict__ dst) {
+  const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  const int64_t total = (int64_t)n_cap * width;
+  GRID_STRIDE(i, total) {
+    const int r = (int)(i / width), c = (int)(i % width);
+    dst[i] = r < n ? src[(int64_t)idx[r] * width + c] : 0.f;
+  }
+}
+
+__global__ void iota_kernel(int32_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+// ------------------------------------------------------------------ MaskROI candidates (mask_roi.py:37-93)
+__global__ void maskroi_candidates_kernel(const float* __restrict__ rois, const float* __restrict__ cls_score,
+                                          const float* __restrict__ bbox_pred, int nroi, const int* __restrict__ nroi_dev,
+                                          int num_classes, float thr, float img_h, float img_w, float* __restrict__ cand,
+                                          int32_t* __restrict__ cand_cls, float* __restrict__ cand_prob,
+                                          int* __restrict__ ncand) {
+  const int nvalid = nroi_dev ? min(*nroi_dev, nroi) : nroi;
+  const int nfg = num_classes - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nroi * nfg) return;
+  const int r = i / nfg, c = i % nfg + 1;
+  float prob = -1.f;
+  float bx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (r < nvalid) {
+    const float* s = cls_score + (int64_t)r * num_classes;
+    float m = s[0];
+    for (int j = 1; j < num_classes; ++j) m = fmaxf(m, s[j]);
+    float sum = 0.f;
+    for (int j = 0; j < num_classes; ++j) sum += expf(s[j] - m);
+    const float p = expf(s[c] - m) / sum;
+    // upsnet bbox_transform (bbox_transform.py:290-330), weights (10,10,5,5), then clip_boxes (:45-60)
+    const float* b = rois + (int64_t)r * 5 + 1;
+    const float* d = bbox_pred + (int64_t)r * num_classes * 4 + c * 4;
+    const float w = b[2] - b[0] + 1.0f, h = b[3] - b[1] + 1.0f;
+    const float cx = b[0] + 0.5f * w, cy = b[1] + 0.5f * h;
+    const float dx = d[0] / 10.0f, dy = d[1] / 10.0f;
+    const float lim = 4.135166556742356f;  // log(1000/16)
+    const float dw = fminf(d[2] / 5.0f, lim), dh = fminf(d[3] / 5.0f, lim);
+    const float pcx = dx * w + cx, pcy = dy * h + cy;
+    const float pw = expf(dw) * w, ph = expf(dh) * h;
+    bx[0] = fmaxf(fminf(pcx - 0.5f * pw, img_w - 1.f), 0.f);
+    bx[1] = fmaxf(fminf(pcy - 0.5f * ph, img_h - 1.f), 0.f);
+    bx[2] = fmaxf(fminf(pcx + 0.5f * pw - 1.f, img_w - 1.f), 0.f);
+    bx[3] = fmaxf(fminf(pcy + 0.5f * ph - 1.f, img_h - 1.f), 0.f);
+    if (p > thr) { prob = p; atomicAdd(ncand, 1); }
+  }
+  float* o = cand + (int64_t)i * 5;
+  o[0] = bx[0]; o[1] = bx[1]; o[2] = bx[2]; o[3] = bx[3]; o[4] = prob;
+  cand_cls[i] = c;
+  cand_prob[i] = prob;
+}
+
+// ------------------------------------------------------------------ tracker
+// dots[i][j] = <emb_i, ref_j>, one warp per pair
+__global__ void track_dot_kernel(const float* __restrict__ emb, const float* __restrict__ ref, int k, int m, int dim,
+                                 float* __restrict__ dots) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pr = warp; pr < (int64_t)k * m; pr += nw) {
+    const int i = (int)(pr / m), j = (int)(pr % m);
+    const float* a = emb + (int64_t)i * dim;
+    const float* b = ref + (int64_t)j * dim;
+    float s = 0.f;
+    for (int c = lane; c < dim; c += 32) s = fmaf(a[c], b[c], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dots[pr] = s;
+  }
+}
+
+// comp scores + row argmax (track_head.py:73-91, panoptic_fusetrack.py:412-424); one warp per detection
+__global__ void track_score_kernel(const float* __restrict__ dots, int k, int m, const float* __restrict__ det_boxes,
+                                   const float* __restrict__ ref_boxes, const int32_t* __restrict__ det_labels,
+                                   const int32_t* __restrict__ ref_labels, const float* __restrict__ cls_prob, float c0,
+                                   float c1, float c2, float* __restrict__ comp, int32_t* __restrict__ match_ids,
+                                   float* __restrict__ match_like) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= k) return;
+  const float* d = dots + (int64_t)i * m;
+  // log_softmax over [0 | dots]
+  float mx = 0.f;
+  for (int j = lane; j < m; j += 32) mx = fmaxf(mx, d[j]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = (lane == 0) ? expf(0.f - mx) : 0.f;
+  for (int j = lane; j < m; j += 32) sum += expf(d[j] - mx);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float lse = mx + logf(sum);
+  const float lp = c0 * logf(cls_prob[i]);
+  const float* a = det_boxes + (int64_t)i * 4;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int j = lane; j <= m; j += 32) {
+    float v;
+    if (j == 0) {
+      v = (0.f - lse) + lp + c1 * 0.f + c2 * 1.f;
+    } else {
+      const float* b = ref_boxes + (int64_t)(j - 1) * 4;
+      const float ltx = fmaxf(a[0], b[0]), lty = fmaxf(a[1], b[1]);
+      const float rbx = fminf(a[2], b[2]), rby = fminf(a[3], b[3]);
+      const float w = fmaxf(rbx - ltx + 1.f, 0.f), h = fmaxf(rby - lty + 1.f, 0.f);
+      const float ov = w * h;
+      const float a1 = (a[2] - a[0] + 1.f) * (a[3] - a[1] + 1.f), a2 = (b[2] - b[0] + 1.f) * (b[3] - b[1] + 1.f);
+      const float iou = ov / (a1 + a2 - ov);
+      const float ld = (ref_labels[j - 1] == det_labels[i]) ? 1.f : 0.f;
+      v = (d[j - 1] - lse) + lp + c1 * iou + c2 * ld;
+    }
+    comp[(int64_t)i * (m + 1) + j] = v;
+    if (v > best) { best = v; besti = j; }   // ascending j per lane => first max per lane
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (lane == 0) { match_ids[i] = besti; match_like[i] = best; }
+}
+
+// the sequential id-assignment loop (panoptic_fusetrack.py:430-469) on one thread.
+// mem_src[slot] = index of the detection whose features/box end up in memory slot `slot` (-1: unchanged).
+__global__ void track_assign_kernel(const int32_t* __restrict__ match_ids, const float* __restrict__ match_like, int k,
+                                    int m, int cap, int32_t* __restrict__ det_obj_ids, int32_t* __restrict__ mem_src,
+                                    float* __restrict__ best_scores, int32_t* __restrict__ best_ids, int* __restrict__ new_m) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int cur = m;
+  for (int j = 0; j < cap; ++j) mem_src[j] = -1;
+  for (int j = 0; j < m; ++j) { best_scores[j] = -100.f; best_ids[j] = -1; }
+  for (int i = 0; i < k; ++i) det_obj_ids[i] = -1;
+  for (int i = 0; i < k; ++i) {
+    const int mid = match_ids[i];
+    if (mid == 0) {
+      if (cur < cap) { det_obj_ids[i] = cur; mem_src[cur] = i; cur++; }
+    } else {
+      const int obj = mid - 1;
+      const float sc = match_like[i];
+      if (sc > best_scores[obj]) {
+        det_obj_ids[i] = obj;
+        if (best_ids[obj] >= 0) det_obj_ids[best_ids[obj]] = -1;
+        best_scores[obj] = sc;
+        best_ids[obj] = i;
+        mem_src[obj] = i;
+      }
+    }
+  }
+  for (int i = 0; i < k; ++i) {
+    if (det_obj_ids[i] >= 0) continue;
+    if (cur < cap) { det_obj_ids[i] = cur; mem_src[cur] = i; cur++; }
+  }
+  *new_m = cur;
+}
+
+}  // namespace
+
+extern "C" int vps_roi_align(const vps_tensor* feats, const int* strides, int nlev, const float* rois, int nroi,
+                             const int* nroi_dev, const vps_tensor* out, int sample_num, void* stream) {
+  VPS_CHECK_ARG(nlev >= 1 && nlev <= MAXLEV && out->h == out->w && out->n >= nroi, "roi_align: args");
+  const int64_t total = (int64_t)nroi * out->h * out->w * out->c;
+  if (!total) return VPS_OK;
+  VPS_DISPATCH_T(out->dtype, T, {
+    Feats<T> fs;
+    fs.n = nlev;
+    for (int i = 0; i < nlev; ++i) {
+      if (feats[i].dtype != out->dtype || feats[i].c < out->c) { vps::set_error("roi_align: level %d dtype/channels", i); return VPS_E_ARG; }
+      fs.l[i] = vps::tv<const T>(feats[i]);
+      fs.scale[i] = 1.0f / (float)strides[i];
+    }
+    roi_align_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(fs, rois, nroi, nroi_dev, vps::tv<T>(*out),
+                                                                          out->h, sample_num, total);
+  });
+  VPS_CUDA_LAST("roi_align");
+  return VPS_OK;
+}
+
+extern "C" int vps_sort_desc(const float* keys, float* keys_out, int32_t* idx_out, int n, void* ws, int64_t ws_bytes,
+                             void* stream) {
+  if (n <= 0) return VPS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, need, keys, keys_out, (const int32_t*)nullptr, idx_out, n, 0, 32, st);
+  const int64_t iota_bytes = ((int64_t)n * 4 + 255) / 256 * 256;
+  VPS_CHECK_ARG(ws_bytes >= (int64_t)need + iota_bytes, "sort_desc: workspace %lld < %lld", (long long)ws_bytes,
+                (long long)(need + iota_bytes));
+  int32_t* iota = (int32_t*)ws;
+  iota_kernel<<<vps::cdiv(n, 256), 256, 0, st>>>(iota, n);
+  VPS_CUDA_LAST("iota");
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending((char*)ws + iota_bytes, need, keys, keys_out, iota, idx_out, n,
+                                                            0, 32, st);
+  if (e != cudaSuccess) { vps::set_error("sort_desc: %s", cudaGetErrorString(e)); return VPS_E_CUDA; }
+  vps::count_launch(3);
+  return VPS_OK;
+}
+
+extern "C" int vps_rpn_decode(const float* scores_sorted, const int32_t* idx_sorted, int k, const vps_tensor* deltas,
+                              int feat_h, int feat_w, int stride, const float* base_anchors, int num_anchors, float img_h,
+                              float img_w, float* dets, void* stream) {
+  if (k <= 0) return VPS_OK;
+  VPS_CHECK_ARG(deltas->h == feat_h && deltas->w == feat_w && deltas->c >= 4 * num_anchors, "rpn_decode: deltas shape");
+  VPS_DISPATCH_T(deltas->dtype, T, (rpn_decode_kernel<T><<<vps::cdiv(k, 128), 128, 0, (cudaStream_t)stream>>>(
+                                       scores_sorted, idx_sorted, k, vps::tv<const T>(*deltas), feat_w, stride,
+                                       base_anchors, num_anchors, img_h, img_w, dets)));
+  VPS_CUDA_LAST("rpn_decode");
+  return VPS_OK;
+}
+
+extern "C" int vps_nms(const float* dets, int n, const int* n_dev, float thr, int32_t* keep_idx, int* nkeep, void* ws,
+                       int64_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) { cudaMemsetAsync(nkeep, 0, sizeof(int), st); return VPS_OK; }
+  const int col_blocks = (n + 63) / 64;
+  VPS_CHECK_ARG(ws_bytes >= (int64_t)n * col_blocks * 8, "nms: workspace too small");
+  VPS_CHECK_ARG(col_blocks * 8 <= 48 * 1024, "nms: n too large");
+  dim3 grid(col_blocks, col_blocks);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(n, n_dev, thr, dets, (unsigned long long*)ws, col_blocks);
+  VPS_CUDA_LAST("nms_mask");
+  nms_reduce_kernel<<<1, 256, col_blocks * 8, st>>>(n, n_dev, (const unsigned long long*)ws, col_blocks, keep_idx, nkeep);
+  VPS_CUDA_LAST("nms_reduce");
+  return VPS_OK;
+}
+
+extern "C" int vps_gather_rows(const float* src, const int32_t* idx, int n, const int* n_dev, int width, float* dst,
+                               void* stream) {
+  if (n <= 0) return VPS_OK;
+  gather_rows_kernel<<<grid_for((int64_t)n * width), 256, 0, (cudaStream_t)stream>>>(src, idx, n, n_dev, width, dst);
+  VPS_CUDA_LAST("gather_rows");
+  return VPS_OK;
+}
+
+extern "C" int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred, int nroi,
+                                      const int* nroi_dev, int num_classes, float score_thr, float img_h, float img_w,
+                                      float* cand, int32_t* cand_cls, float* cand_prob, int* ncand, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(ncand, 0, sizeof(int), st);
+  const int total = nroi * (num_classes - 1);
+  if (total <= 0) return VPS_OK;
+  maskroi_candidates_kernel<<<vps::cdiv(total, 128), 128, 0, st>>>(rois, cls_score, bbox_pred, nroi, nroi_dev, num_classes,
+                                                                 score_thr, img_h, img_w, cand, cand_cls, cand_prob, ncand);
+  VPS_CUDA_LAST("maskroi_candidates");
+  return VPS_OK;
+}
+
+// ws layout (floats/ints): dots[k*m] | match_like[k] | best_scores[cap] | best_ids[cap]
+extern "C" int vps_track_assign(const float* emb, const float* ref_emb, int k, int m, int dim, const float* det_boxes,
+                                const float* ref_boxes, const int32_t* det_labels, const int32_t* ref_labels,
+                                const float* cls_prob, float c0, float c1, float c2, int cap, int32_t* det_obj_ids,
+                                int32_t* match_ids, float* comp_scores, int32_t* mem_src, int* new_m, void* ws,
+                                int64_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  VPS_CHECK_ARG(k >= 1 && m >= 1 && m <= cap, "track_assign: k %d m %d cap %d", k, m, cap);
+  const int64_t need = ((int64_t)k * m + k + 2 * cap) * 4;
+  VPS_CHECK_ARG(ws_bytes >= need, "track_assign: workspace %lld < %lld", (long long)ws_bytes, (long long)need);
+  float* dots = (float*)ws;
+  float* match_like = dots + (int64_t)k * m;
+  float* best_scores = match_like + k;
+  int32_t* best_ids = (int32_t*)(best_scores + cap);
+  track_dot_kernel<<<grid_for((int64_t)k * m * 32), 256, 0, st>>>(emb, ref_emb, k, m, dim, dots);
+  VPS_CUDA_LAST("track_dot");
+  track_score_kernel<<<vps::cdiv((int64_t)k * 32, 128), 128, 0, st>>>(dots, k, m, det_boxes, ref_boxes, det_labels,
+                                                                     ref_labels, cls_prob, c0, c1, c2, comp_scores,
+                                                                     match_ids, match_like);
+  VPS_CUDA_LAST("track_score");
+  track_assign_kernel<<<1, 32, 0, st>>>(match_ids, match_like, k, m, cap, det_obj_ids, mem_src, best_scores, best_ids, new_m);
+  VPS_CUDA_LAST("track_assign");
+  return VPS_OK;
+}

@@ -1,0 +1,254 @@
+// Panoptic fusion kernels: MaskRemoval (mask_removal.py:29-92) and the final per-pixel fusion
+// (SegTerm unary_logits.py:81-108 + mask paste mask_removal.py:86 + argmax panoptic_fusetrack.py:588-593).
+// Neither the [1,k,H,W] mask_energy tensor nor the [1,11+k,H,W] logits tensor of the reference is
+// ever materialised: resized mask logits are recomputed from the 28x28 maps wherever they are needed.
+#include "common.cuh"
+
+namespace {
+
+// cv2.resize(src[ms x ms] f32, (w, h), INTER_LINEAR) value at (dy, dx): half-pixel centres, taps clamped
+// with the fractional weight zeroed at the borders (OpenCV resize.cpp linear coefficient tables).
+__device__ __forceinline__ float cv_resize_linear(const float* __restrict__ src, int ms, int w, int h, int dy, int dx) {
+  const double scale_x = (double)ms / (double)w, scale_y = (double)ms / (double)h;
+  float fx = (float)(((double)dx + 0.5) * scale_x - 0.5);
+  int sx = (int)floorf(fx);
+  fx -= (float)sx;
+  if (sx < 0) { fx = 0.f; sx = 0; }
+  if (sx >= ms - 1) { fx = 0.f; sx = ms - 1; }
+  float fy = (float)(((double)dy + 0.5) * scale_y - 0.5);
+  int sy = (int)floorf(fy);
+  fy -= (float)sy;
+  if (sy < 0) { fy = 0.f; sy = 0; }
+  if (sy >= ms - 1) { fy = 0.f; sy = ms - 1; }
+  const int sx1 = min(sx + 1, ms - 1), sy1 = min(sy + 1, ms - 1);
+  const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+  const float r0 = src[sy * ms + sx] * a0 + src[sy * ms + sx1] * a1;
+  const float r1 = src[sy1 * ms + sx] * a0 + src[sy1 * ms + sx1] * a1;
+  return r0 * b0 + r1 * b1;
+}
+
+struct BoxI { int x1, y1, x2, y2, w, h, x_0, x_1, y_0, y_1; };
+__device__ __forceinline__ BoxI int_box(const float* b, int H, int W) {
+  BoxI r;
+  r.x1 = (int)b[0]; r.y1 = (int)b[1]; r.x2 = (int)b[2]; r.y2 = (int)b[3];   // astype(np.int32): trunc toward 0
+  r.w = max(r.x2 - r.x1 + 1, 1); r.h = max(r.y2 - r.y1 + 1, 1);
+  r.x_0 = max(r.x1, 0); r.x_1 = min(r.x2 + 1, W);
+  r.y_0 = max(r.y1, 0); r.y_1 = min(r.y2 + 1, H);
+  return r;
+}
+
+// pass A for sorted position `pos`: count mask pixels and pixels already claimed by the same class
+__global__ void mr_count_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ order, int pos, int k,
+                                const int* __restrict__ k_dev, const float* __restrict__ mask_logit, int ms,
+                                const int32_t* __restrict__ cls_idx, int H, int W, const uint8_t* __restrict__ occ,
+                                unsigned int* __restrict__ counters) {
+  const int kk = k_dev ? min(*k_dev, k) : k;
+  if (pos >= kk) return;
+  const int det = order[pos];
+  const int cls = cls_idx[det] - 1;
+  if (cls < 0) return;
+  const BoxI b = int_box(boxes + (int64_t)det * 4, H, W);
+  const int cw = b.x_1 - b.x_0, ch = b.y_1 - b.y_0;
+  if (cw <= 0 || ch <= 0) return;
+  const float* ml = mask_logit + (int64_t)det * ms * ms;
+  const uint8_t* oc = occ + (int64_t)cls * H * W;
+  unsigned int msum = 0, osum = 0;
+  const int64_t total = (int64_t)cw * ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
+    const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
+    if (v > 0.f) {
+      msum++;
+      if (oc[(int64_t)y * W + x] >= 1) osum++;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { msum += __shfl_xor_sync(0xffffffffu, msum, o); osum += __shfl_xor_sync(0xffffffffu, osum, o); }
+  if ((threadIdx.x & 31) == 0 && (msum | osum)) {
+    atomicAdd(counters + 2 * pos, msum);
+    atomicAdd(counters + 2 * pos + 1, osum);
+  }
+}
+
+// pass B: decide keep (mask_removal.py:81-83) and, if kept, add the mask into the class occupancy image
+__global__ void mr_apply_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ order, int pos, int k,
+                                const int* __restrict__ k_dev, const float* __restrict__ mask_logit, int ms,
+                                const int32_t* __restrict__ cls_idx, int H, int W, float frac_thr, uint8_t* __restrict__ occ,
+                                const unsigned int* __restrict__ counters, int32_t* __restrict__ keep_flag) {
+  const int kk = k_dev ? min(*k_dev, k) : k;
+  if (pos >= kk) return;
+  const int det = order[pos];
+  const int cls = cls_idx[det] - 1;
+  const unsigned int msum = counters[2 * pos], osum = counters[2 * pos + 1];
+  // numpy: int / int -> float64 true division compared with the python float 0.3
+  const bool keep = cls >= 0 && msum != 0 && !((double)osum / (double)msum > (double)frac_thr);
+  if (blockIdx.x == 0 && threadIdx.x == 0) keep_flag[pos] = keep ? 1 : 0;
+  if (!keep) return;
+  const BoxI b = int_box(boxes + (int64_t)det * 4, H, W);
+  const int cw = b.x_1 - b.x_0, ch = b.y_1 - b.y_0;
+  const float* ml = mask_logit + (int64_t)det * ms * ms;
+  uint8_t* oc = occ + (int64_t)cls * H * W;
+  const int64_t total = (int64_t)cw * ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
+    const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
+    if (v > 0.f) oc[(int64_t)y * W + x] += 1;   // uint8 += (wraps like numpy)
+  }
+}
+
+// compact kept detections in sorted order: keep_sorted[j] = det index of the j-th kept one
+__global__ void mr_compact_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ keep_flag, int k,
+                                  const int* __restrict__ k_dev, int32_t* __restrict__ keep_sorted, int* __restrict__ nkeep) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int kk = k_dev ? min(*k_dev, k) : k;
+  int n = 0;
+  for (int i = 0; i < kk; ++i)
+    if (keep_flag[i]) keep_sorted[n++] = order[i];
+  *nkeep = n;
+}
+
+// ------------------------------------------------------------------ final fusion
+constexpr int MAX_INST = 128;
+struct InstParams {
+  // SegTerm box (unary_logits.py:99-103) and paste box (mask_removal.py:59-86), per kept instance
+  int sy0[MAX_INST], sy1[MAX_INST], sx0[MAX_INST], sx1[MAX_INST];
+  int bx1[MAX_INST], by1[MAX_INST], bw[MAX_INST], bh[MAX_INST], px0[MAX_INST], px1[MAX_INST], py0[MAX_INST], py1[MAX_INST];
+  int seg_ch[MAX_INST];   // channel of fcn_output feeding inst_seg, -1 for the dummy instance
+  int det[MAX_INST];
+};
+
+__global__ void fuse_prepare_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ cls_idx,
+                                    const int32_t* __restrict__ keep_sorted, const int* __restrict__ nkeep_dev, int kcap,
+                                    int num_stuff, int H, int W, InstParams* __restrict__ ip, int* __restrict__ ninst) {
+  const int j = threadIdx.x;
+  int nk = min(*nkeep_dev, kcap);
+  if (j == 0) *ninst = nk;
+  if (j >= nk) return;
+  const int det = keep_sorted[j];
+  const float* b = boxes + (int64_t)det * 4;
+  const int cls = cls_idx[det];
+  ip->det[j] = det;
+  ip->seg_ch[j] = cls > 0 ? (num_stuff - 1 + cls) : -1;   // class_mapping {1..8 -> 11..18} (fusetrack.py:148)
+  // SegTerm: boxes*(1/4) of mask_rois*4 is exact; y0=int(y1), y1=int(round(y2)+1) (np.round = half-to-even)
+  ip->sy0[j] = (int)b[1]; ip->sy1[j] = (int)(rintf(b[3]) + 1.f);
+  ip->sx0[j] = (int)b[0]; ip->sx1[j] = (int)(rintf(b[2]) + 1.f);
+  const BoxI r = int_box(b, H, W);
+  ip->bx1[j] = r.x1; ip->by1[j] = r.y1; ip->bw[j] = r.w; ip->bh[j] = r.h;
+  ip->px0[j] = r.x_0; ip->px1[j] = r.x_1; ip->py0[j] = r.y_0; ip->py1[j] = r.y_1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) panoptic_fuse_kernel(vps::TV<const T> score, const float* __restrict__ mask_logit,
+                                                            int ms, const InstParams* __restrict__ ipg,
+                                                            const int* __restrict__ ninst_dev, int num_stuff, int dummy,
+                                                            int H, int W, int64_t* __restrict__ pano,
+                                                            int64_t* __restrict__ sem) {
+  __shared__ InstParams ip;
+  {
+    const int* src = (const int*)ipg;
+    int* dst = (int*)&ip;
+    for (int i = threadIdx.x; i < (int)(sizeof(InstParams) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int ninst = *ninst_dev;
+  const int NC = score.c;
+  const float sy = (float)score.h / (float)H, sx = (float)score.w / (float)W;
+  const int64_t total = (int64_t)H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W), Y = (int)(i / W);
+    // fcn_output = bilinear x4 (align_corners False) of fcn_score (upsnetFPN.py:59,80)
+    const float fy = fmaxf(sy * ((float)Y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)X + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < score.h - 1 ? 1 : 0), x1 = x0 + (x0 < score.w - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const T* p00 = score.p + score.off(0, y0, x0);
+    const T* p01 = score.p + score.off(0, y0, x1);
+    const T* p10 = score.p + score.off(0, y1, x0);
+    const T* p11 = score.p + score.off(0, y1, x1);
+    float fo[24];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) {
+      if (c < NC)
+        fo[c] = hy * (hx * vps::ldf<T>(p00 + c) + lx * vps::ldf<T>(p01 + c)) +
+                ly * (hx * vps::ldf<T>(p10 + c) + lx * vps::ldf<T>(p11 + c));
+      else
+        fo[c] = -INFINITY;
+    }
+    // semantic argmax (first max)
+    float bs = fo[0]; int bsi = 0;
+#pragma unroll
+    for (int c = 1; c < 24; ++c) if (c < NC && fo[c] > bs) { bs = fo[c]; bsi = c; }
+    sem[i] = bsi;
+    // panoptic argmax over [stuff | instances]
+    float bp = fo[0]; int bpi = 0;
+#pragma unroll
+    for (int c = 1; c < 24; ++c) if (c < num_stuff && fo[c] > bp) { bp = fo[c]; bpi = c; }
+    if (dummy) {
+      // MaskROI dummy detection (mask_roi.py:136-142): one all-zero instance channel
+      if (0.f > bp) { bp = 0.f; bpi = num_stuff; }
+    } else {
+      for (int j = 0; j < ninst; ++j) {
+        float v = 0.f;
+        if (ip.seg_ch[j] >= 0 && Y >= ip.sy0[j] && Y < ip.sy1[j] && X >= ip.sx0[j] && X < ip.sx1[j]) {
+          float s = 0.f;
+          const int ch = ip.seg_ch[j];
+#pragma unroll
+          for (int c = 0; c < 24; ++c) if (c == ch) s = fo[c];
+          v = s;
+        }
+        if (Y >= ip.py0[j] && Y < ip.py1[j] && X >= ip.px0[j] && X < ip.px1[j])
+          v += cv_resize_linear(mask_logit + (int64_t)ip.det[j] * ms * ms, ms, ip.bw[j], ip.bh[j], Y - ip.by1[j], X - ip.bx1[j]);
+        if (v > bp) { bp = v; bpi = num_stuff + j; }
+      }
+    }
+    pano[i] = bpi;
+  }
+}
+
+InstParams* g_ip = nullptr;
+int* g_ninst = nullptr;
+
+}  // namespace
+
+extern "C" int vps_mask_removal(const float* boxes, const int32_t* order, int k, const int* k_dev,
+                                const float* mask_logit, int msize, const int32_t* cls_idx, int H, int W, float frac_thr,
+                                uint8_t* occ, int num_things, unsigned int* counters, int32_t* keep_flag,
+                                int32_t* keep_sorted, int* nkeep, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(occ, 0, (size_t)num_things * H * W, st);
+  cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 2 * k, st);
+  cudaMemsetAsync(keep_flag, 0, sizeof(int32_t) * k, st);
+  for (int pos = 0; pos < k; ++pos) {
+    mr_count_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, occ, counters);
+    mr_apply_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, frac_thr, occ,
+                                         counters, keep_flag);
+  }
+  mr_compact_kernel<<<1, 32, 0, st>>>(order, keep_flag, k, k_dev, keep_sorted, nkeep);
+  VPS_CUDA_LAST("mask_removal");
+  vps::count_launch(2 * k);
+  return VPS_OK;
+}
+
+extern "C" int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes, const int32_t* cls_idx,
+                                 const float* mask_logit, int msize, const int32_t* keep_sorted, const int* nkeep_dev,
+                                 int kcap, int num_stuff, int dummy, int H, int W, int64_t* pano_out, int64_t* sem_out,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  VPS_CHECK_ARG(fcn_score->c <= 24 && kcap <= MAX_INST && fcn_score->n == 1, "panoptic_fuse: args (c %d kcap %d)", fcn_score->c, kcap);
+  if (!g_ip) {
+    if (cudaMalloc(&g_ip, sizeof(InstParams)) != cudaSuccess || cudaMalloc(&g_ninst, sizeof(int)) != cudaSuccess) {
+      vps::set_error("panoptic_fuse: malloc");
+      return VPS_E_CUDA;
+    }
+  }
+  if (dummy) {
+    cudaMemsetAsync(g_ninst, 0, sizeof(int), st);
+  } else {
+    fuse_prepare_kernel<<<1, MAX_INST, 0, st>>>(boxes, cls_idx, keep_sorted, nkeep_dev, kcap, num_stuff, H, W, g_ip, g_ninst);
+    VPS_CUDA_LAST("fuse_prepare");
+  }
+  VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T><<<148 * 4, 256, 0, st>>>(
+                                          vps::tv<const T>(*fcn_score), mask_logit, msize, g_ip, g_ninst, num_stuff, dummy, H,
+                                          W, pano_out, sem_out)));
+  VPS_CUDA_LAST("panoptic_fuse");
+  return VPS_OK;
+}
