@@ -111,6 +111,12 @@ int vps_resample2d(const vps_tensor* src, const vps_tensor* flow, const vps_tens
  * computes the norm of (a - b) when b != NULL (fuses flownet2.py:147-148). out has 1 channel. */
 int vps_channelnorm(const vps_tensor* a, const vps_tensor* b, const vps_tensor* out, void* stream);
 
+/* compute_flow head (panoptic_fusetrack.py:119-121 denormalize, flownet2.py:135-139): rgb = img*std+mean
+ * for both NCHW fp32 frames, per-channel mean over both frames, x = (rgb - mean)/rgb_max -> NHWC [1,H,W,6]
+ * (img 0..2, ref 3..5).  std3/mean3 are HOST arrays of 3 floats; sums_ws = 3 device doubles. */
+int vps_flownet_input(const float* img_nchw, const float* ref_nchw, int H, int W, const float* std3,
+                      const float* mean3, float rgb_max, double* sums_ws, const vps_tensor* x, void* stream);
+
 /* ---- layout / pointwise / resampling --------------------------------------------------------- */
 int vps_nchw_to_nhwc(const float* src, const vps_tensor* dst, void* stream);   /* src [n,c,h,w] f32 */
 int vps_nhwc_to_nchw(const vps_tensor* src, float* dst, void* stream);
@@ -187,7 +193,8 @@ int vps_gather_rows(const float* src, const int32_t* idx, int n, const int* n_de
  * clip_boxes :45-60): slot (roi*8 + class-1) of cand [nroi*8,5] gets the decoded, clipped box and
  * softmax prob if prob > score_thr, else prob = -1 (class-agnostic fold order, deterministic);
  * *ncand = number of valid slots. */
-int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred, int nroi,
+int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred,
+                           int row_stride /* floats between consecutive RoI rows of cls_score / bbox_pred */, int nroi,
                            const int* nroi_dev, int num_classes, float score_thr, float img_h, float img_w,
                            float* cand, int32_t* cand_cls, float* cand_prob, int* ncand, void* stream);
 /* tracker (track_head.py:73-132, panoptic_fusetrack.py:412-469): dots = emb . ref_emb^T,
@@ -200,6 +207,31 @@ int vps_track_assign(const float* emb, const float* ref_emb, int k, int m, int d
                      const float* cls_prob, float c0, float c1, float c2, int cap, int32_t* det_obj_ids,
                      int32_t* match_ids, float* comp_scores, int32_t* mem_src, int* new_m, void* ws,
                      int64_t ws_bytes, void* stream);
+
+/* RPN tail (rpn_head.py:94-103): dets_cat = nlev segments of `seg` rows [x1,y1,x2,y2,score] with counts[l]
+ * valid rows each; stable top-`cap` by score -> proposals [cap,5] and rois [cap,5] = (0,x1,y1,x2,y2)
+ * (bbox2roi, transforms.py:106-125); *total = min(cap, sum counts).  Workspaces: scores_ws/scores_sorted_ws
+ * [nlev*seg] f32, idx_sorted_ws [nlev*seg] i32, sort_ws as for vps_sort_desc. */
+int vps_rpn_finalize(const float* dets_cat, const int* counts, int nlev, int seg, int cap, float* scores_ws,
+                     float* scores_sorted_ws, int32_t* idx_sorted_ws, void* sort_ws, int64_t sort_ws_bytes,
+                     float* proposals, float* rois, int* total, void* stream);
+/* MaskROI tail (mask_roi.py:95-147): NMS survivors `keep[0..*nkeep)` (positions in the score-sorted candidate
+ * list) -> max_det rule (scores >= the max_det-th best) -> det_rois [cap,5] (batch 0), cls_idx, cls_prob;
+ * kout[0] = k, kout[1] = 1 when the dummy "no detection" result (score 1, zero box, class 0) was emitted. */
+int vps_maskroi_finalize(const float* cand_sorted, const int32_t* slot_sorted, const int32_t* cand_cls,
+                         const int32_t* keep, const int* nkeep, int max_det, int cap, float* det_rois,
+                         int32_t* cls_idx, float* cls_prob, int* kout, void* stream);
+/* det_bboxes = roi2bbox(det_rois) (transforms.py:128-135) and det_labels = cls_idx - 1
+ * (panoptic_fusetrack.py:386-389): det_rois [cap,5] -> boxes [cap,4], labels [cap]. */
+int vps_det_split(const float* det_rois, const int32_t* cls_idx, int cap, float* boxes, int32_t* labels,
+                  void* stream);
+/* mask_score.gather(1, cls_idx) (panoptic_fusetrack.py:566-568): logits NHWC [>=k,ms,ms,9] -> out f32 [k,ms,ms] */
+int vps_select_class(const vps_tensor* logits, const int32_t* cls_idx, int k, float* out, void* stream);
+/* tracker memory update (panoptic_fusetrack.py:441-443,458-459,467-469): for j < *new_m with mem_src[j] >= 0:
+ * mem_feats[j] <- det_feats[mem_src[j]], mem_boxes likewise, mem_labels only for appended slots (j >= old_m). */
+int vps_track_update(void* mem_feats, const void* det_feats, int dtype, int64_t feat_len, float* mem_boxes,
+                     const float* det_boxes, int32_t* mem_labels, const int32_t* det_labels,
+                     const int32_t* mem_src, int old_m, int cap, const int* new_m_dev, void* stream);
 
 /* ---- panoptic fusion ------------------------------------------------------------------------- */
 /* MaskRemoval (mask_removal.py:29-92): boxes [k,4] f32, mask_logit [k,ms,ms] f32, cls_idx[k] (1-based),

@@ -1,0 +1,109 @@
+"""CPU: the drop-in boundary -- registries, config loader, state_dict layout, C-ABI exports, no-fallback rule."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = "/root/reference/configs/cityscapes/fusetrack.py"
+
+
+def test_registry_semantics_match_reference():
+    from vps_b200.registry import Registry, build_from_cfg
+    r = Registry("thing")
+
+    @r.register_module
+    class A(object):
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+    with pytest.raises(KeyError):          # duplicate name (mmdet/utils/registry.py:40-43)
+        r.register_module(A)
+    with pytest.raises(TypeError):
+        r.register_module(3)
+    obj = build_from_cfg(dict(type="A", x=1), r, default_args=dict(y=5, x=9))
+    assert (obj.x, obj.y) == (1, 5)        # cfg wins over default_args (setdefault)
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(type="Nope"), r)
+    assert r.get("A") is A and r.get("B") is None and "A" in r.module_dict
+
+
+def test_all_reference_names_are_registered():
+    import vps_b200 as V
+    assert V.DETECTORS.get("PanopticFuseTrack") is not None
+    for reg, names in ((V.BACKBONES, ["ResNet"]), (V.NECKS, ["FPN"]), (V.EXTRA_NECKS, ["BFPTcea"]),
+                       (V.PANOPTIC, ["UPSNetFPN"]), (V.ROI_EXTRACTORS, ["SingleRoIExtractor"]),
+                       (V.HEADS, ["RPNHead", "SharedFCBBoxHead", "TrackHead", "FCNMaskHead"]),
+                       (V.LOSSES, ["CrossEntropyLoss", "SmoothL1Loss"])):
+        for n in names:
+            assert reg.get(n) is not None, n
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference tree not mounted")
+def test_reference_config_loads_unmodified_and_builds():
+    from vps_b200 import Config, build_detector, fusetrack_cfg
+    cfg = Config.fromfile(REF_CFG)
+    assert hasattr(cfg.test_cfg, "flownet2") and not hasattr(cfg.test_cfg, "nope")
+    assert cfg.test_cfg.rpn.nms_thr == 0.7 and cfg.model.bbox_head.num_classes == 9
+    det = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+    mine = fusetrack_cfg()
+    ref_model = {k: v for k, v in cfg.model.items()}
+    ref_model["pretrained"] = None
+    assert _plain(ref_model) == _plain(mine["model"])
+    assert _plain(cfg.test_cfg) == _plain(mine["test_cfg"])
+    assert det.class_mapping == {i: 10 + i for i in range(1, 9)}
+
+
+def _plain(x):
+    if isinstance(x, dict):
+        return {k: _plain(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_plain(v) for v in x]
+    return x
+
+
+def test_state_dict_layout_matches_oracle_and_reference_names():
+    from oracle.model import PanopticFuseTrack as Oracle
+    from vps_b200 import ConfigDict, build_detector, fusetrack_cfg
+    c = fusetrack_cfg()
+    det = build_detector(ConfigDict(c["model"]), train_cfg=None, test_cfg=ConfigDict(c["test_cfg"]))
+    o = Oracle()
+    a, b = det.state_dict(), o.state_dict()
+    assert set(a) == set(b)
+    assert all(a[k].shape == b[k].shape for k in a)
+    det.load_state_dict(b, strict=True)
+    for k in ("backbone.layer1.0.downsample.0.weight", "neck.lateral_convs.3.conv.bias",
+              "extra_neck.liteflownet.flow_estimator.convs.2.0.weight", "extra_neck.tcea_fusion.sAtt_add_2.bias",
+              "extra_neck.refine.conv.weight", "panopticFPN.deform_convs.0.3.conv_offset.weight",
+              "panopticFPN.deform_convs.0.6.conv.weight", "panopticFPN.deform_convs.0.7.bias",
+              "panopticFPN.conv_pred.conv.weight", "rpn_head.rpn_reg.bias", "bbox_head.shared_fcs.1.weight",
+              "track_head.fcs.0.weight", "mask_head.convs.3.conv.weight", "mask_head.upsample.weight",
+              "flownet2.flownetc.conv_redir.0.weight", "flownet2.flownets_2.upsampled_flow6_to_5.weight",
+              "flownet2.flownets_d.inter_conv3.0.bias", "flownet2.flownetfusion.predict_flow0.weight"):
+        assert k in a, k
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from vps_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vps_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:const char\*|int64_t|int)\s+(vps_[a-z0-9_]+)\s*\(", hdr, re.M))
+    assert len(declared) >= 40
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.vps_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA: no oracle / torch fallback."""
+    from vps_b200 import ConfigDict, build_detector, fusetrack_cfg
+    c = fusetrack_cfg()
+    det = build_detector(ConfigDict(c["model"]), train_cfg=None, test_cfg=ConfigDict(c["test_cfg"]))
+    img = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(Exception):
+        det.simple_test(img, [dict(filename="city", iid=1, img_shape=(64, 64, 3))], ref_img=[img])
+    src = "".join(open(os.path.join(ROOT, "vps_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "vps_b200"))
+                  if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src

@@ -61,12 +61,13 @@ EXPORTS = [
     "vps_last_error", "vps_version", "vps_launch_count",
     "vps_conv2d_tc", "vps_conv2d_simt", "vps_pack_weights_tc", "vps_pack_weights_simt",
     "vps_packed_tc_bytes", "vps_im2col",
-    "vps_correlation", "vps_resample2d", "vps_channelnorm",
+    "vps_correlation", "vps_resample2d", "vps_channelnorm", "vps_flownet_input",
     "vps_nchw_to_nhwc", "vps_nhwc_to_nchw", "vps_copy_scale", "vps_axpby",
     "vps_resize_bilinear", "vps_resize_nearest", "vps_pool2d", "vps_groupnorm",
     "vps_bfp_gather", "vps_bfp_scatter", "vps_flow_warp", "vps_tcea_temporal", "vps_tcea_combine",
     "vps_deform_im2col",
     "vps_roi_align", "vps_sort_desc", "vps_rpn_decode", "vps_nms", "vps_sigmoid_flat", "vps_gather_rows",
     "vps_maskroi_candidates", "vps_track_assign",
+    "vps_rpn_finalize", "vps_maskroi_finalize", "vps_select_class", "vps_track_update", "vps_det_split",
     "vps_mask_removal", "vps_panoptic_fuse",
 ]

@@ -186,7 +186,8 @@ __global__ void iota_kernel(int32_t* p, int n) {
 
 // ------------------------------------------------------------------ MaskROI candidates (mask_roi.py:37-93)
 __global__ void maskroi_candidates_kernel(const float* __restrict__ rois, const float* __restrict__ cls_score,
-                                          const float* __restrict__ bbox_pred, int nroi, const int* __restrict__ nroi_dev,
+                                          const float* __restrict__ bbox_pred, int row_stride, int nroi,
+                                          const int* __restrict__ nroi_dev,
                                           int num_classes, float thr, float img_h, float img_w, float* __restrict__ cand,
                                           int32_t* __restrict__ cand_cls, float* __restrict__ cand_prob,
                                           int* __restrict__ ncand) {
@@ -198,7 +199,7 @@ __global__ void maskroi_candidates_kernel(const float* __restrict__ rois, const 
   float prob = -1.f;
   float bx[4] = {0.f, 0.f, 0.f, 0.f};
   if (r < nvalid) {
-    const float* s = cls_score + (int64_t)r * num_classes;
+    const float* s = cls_score + (int64_t)r * row_stride;
     float m = s[0];
     for (int j = 1; j < num_classes; ++j) m = fmaxf(m, s[j]);
     float sum = 0.f;
@@ -206,7 +207,7 @@ __global__ void maskroi_candidates_kernel(const float* __restrict__ rois, const 
     const float p = expf(s[c] - m) / sum;
     // upsnet bbox_transform (bbox_transform.py:290-330), weights (10,10,5,5), then clip_boxes (:45-60)
     const float* b = rois + (int64_t)r * 5 + 1;
-    const float* d = bbox_pred + (int64_t)r * num_classes * 4 + c * 4;
+    const float* d = bbox_pred + (int64_t)r * row_stride + c * 4;
     const float w = b[2] - b[0] + 1.0f, h = b[3] - b[1] + 1.0f;
     const float cx = b[0] + 0.5f * w, cy = b[1] + 0.5f * h;
     const float dx = d[0] / 10.0f, dy = d[1] / 10.0f;
@@ -325,6 +326,111 @@ __global__ void track_assign_kernel(const int32_t* __restrict__ match_ids, const
   *new_m = cur;
 }
 
+
+// ------------------------------------------------------------------ small glue kernels (device-side bookkeeping)
+// RPN: concatenated per-level kept proposals -> final stable top-k (rpn_head.py:94-103).  dets_cat holds
+// nlev segments of `seg` rows; segment l has counts[l] valid rows.  Writes compact scores for sorting.
+__global__ void rpn_concat_scores_kernel(const float* __restrict__ dets_cat, const int* __restrict__ counts, int nlev,
+                                         int seg, float* __restrict__ scores, int* __restrict__ total, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    int t = 0;
+    for (int l = 0; l < nlev; ++l) t += min(counts[l], seg);
+    *total = min(t, cap);
+  }
+  if (i >= nlev * seg) return;
+  const int l = i / seg, r = i % seg;
+  scores[i] = (r < min(counts[l], seg)) ? dets_cat[(int64_t)i * 5 + 4] : -1.0f;   // sigmoid scores are > 0
+}
+__global__ void rpn_finalize_kernel(const float* __restrict__ dets_cat, const int32_t* __restrict__ idx_sorted,
+                                    const int* __restrict__ total, int cap, float* __restrict__ proposals,
+                                    float* __restrict__ rois) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (i < *total) {
+    const float* s = dets_cat + (int64_t)idx_sorted[i] * 5;
+    for (int j = 0; j < 5; ++j) v[j] = s[j];
+  }
+  for (int j = 0; j < 5; ++j) proposals[(int64_t)i * 5 + j] = v[j];
+  rois[(int64_t)i * 5] = 0.f;   // bbox2roi batch index (transforms.py:106-125)
+  for (int j = 0; j < 4; ++j) rois[(int64_t)i * 5 + 1 + j] = v[j];
+}
+
+// MaskROI tail (mask_roi.py:95-147): NMS survivors (score order) -> max_det rule (keep scores >= the
+// max_det-th best) -> det_rois [cap,5] (batch 0), cls_idx, cls_prob; dummy result when nothing survives.
+__global__ void maskroi_finalize_kernel(const float* __restrict__ cand_sorted, const int32_t* __restrict__ slot_sorted,
+                                        const int32_t* __restrict__ cand_cls, const int32_t* __restrict__ keep,
+                                        const int* __restrict__ nkeep, int max_det, int cap, float* __restrict__ det_rois,
+                                        int32_t* __restrict__ cls_idx, float* __restrict__ cls_prob, int* __restrict__ kout) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int n = *nkeep;
+  if (max_det > 0 && n > max_det) {
+    const float thresh = cand_sorted[(int64_t)keep[max_det - 1] * 5 + 4];
+    int m = max_det;
+    while (m < n && cand_sorted[(int64_t)keep[m] * 5 + 4] >= thresh) ++m;
+    n = m;
+  }
+  if (n > cap) n = cap;
+  for (int i = 0; i < cap; ++i) {
+    float* r = det_rois + (int64_t)i * 5;
+    if (i < n) {
+      const float* c = cand_sorted + (int64_t)keep[i] * 5;
+      r[0] = 0.f; r[1] = c[0]; r[2] = c[1]; r[3] = c[2]; r[4] = c[3];
+      cls_prob[i] = c[4];
+      cls_idx[i] = cand_cls[slot_sorted[keep[i]]];
+    } else {
+      r[0] = r[1] = r[2] = r[3] = r[4] = 0.f;
+      cls_prob[i] = 0.f; cls_idx[i] = 0;
+    }
+  }
+  if (n == 0) {            // dummy detection (mask_roi.py:136-142): score 1, zero box, class 0
+    cls_prob[0] = 1.f; cls_idx[0] = 0;
+    kout[0] = 1; kout[1] = 1;
+  } else {
+    kout[0] = n; kout[1] = 0;
+  }
+}
+
+// mask_score.gather(1, cls_idx) (panoptic_fusetrack.py:566-568): pick the class channel of each RoI's 28x28x9 logits
+template <typename T>
+__global__ void select_class_kernel(vps::TV<const T> logits, const int32_t* __restrict__ cls_idx, int k,
+                                    float* __restrict__ out) {
+  const int64_t per = (int64_t)logits.h * logits.w;
+  const int64_t total = (int64_t)k * per;
+  GRID_STRIDE(i, total) {
+    const int r = (int)(i / per);
+    const int64_t pix = i % per;
+    out[i] = vps::ldf<T>(logits.p + ((int64_t)r * per + pix) * logits.cs + cls_idx[r]);
+  }
+}
+
+// tracker memory update (panoptic_fusetrack.py:441-443,458-459,467-469): slot j <- detection mem_src[j]
+template <typename T>
+__global__ void track_update_kernel(T* __restrict__ mem_feats, const T* __restrict__ det_feats, int64_t feat_len,
+                                    float* __restrict__ mem_boxes, const float* __restrict__ det_boxes,
+                                    int32_t* __restrict__ mem_labels, const int32_t* __restrict__ det_labels,
+                                    const int32_t* __restrict__ mem_src, int old_m, const int* __restrict__ new_m_dev) {
+  const int j = blockIdx.y;
+  if (j >= *new_m_dev) return;
+  const int src = mem_src[j];
+  if (src < 0) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < feat_len; i += (int64_t)gridDim.x * blockDim.x)
+    mem_feats[(int64_t)j * feat_len + i] = det_feats[(int64_t)src * feat_len + i];
+  if (blockIdx.x == 0 && threadIdx.x < 4) mem_boxes[(int64_t)j * 4 + threadIdx.x] = det_boxes[(int64_t)src * 4 + threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && j >= old_m) mem_labels[j] = det_labels[src];
+}
+
+
+// det_bboxes = roi2bbox(det_rois) (transforms.py:128-135), det_labels = cls_idx - 1 (panoptic_fusetrack.py:386)
+__global__ void det_split_kernel(const float* __restrict__ det_rois, const int32_t* __restrict__ cls_idx, int cap,
+                                 float* __restrict__ boxes, int32_t* __restrict__ labels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  for (int j = 0; j < 4; ++j) boxes[i * 4 + j] = det_rois[i * 5 + 1 + j];
+  labels[i] = cls_idx[i] - 1;
+}
+
 }  // namespace
 
 extern "C" int vps_roi_align(const vps_tensor* feats, const int* strides, int nlev, const float* rois, int nroi,
@@ -401,14 +507,14 @@ extern "C" int vps_gather_rows(const float* src, const int32_t* idx, int n, cons
   return VPS_OK;
 }
 
-extern "C" int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred, int nroi,
-                                      const int* nroi_dev, int num_classes, float score_thr, float img_h, float img_w,
+extern "C" int vps_maskroi_candidates(const float* rois, const float* cls_score, const float* bbox_pred,
+                                      int row_stride, int nroi, const int* nroi_dev, int num_classes, float score_thr, float img_h, float img_w,
                                       float* cand, int32_t* cand_cls, float* cand_prob, int* ncand, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(ncand, 0, sizeof(int), st);
   const int total = nroi * (num_classes - 1);
   if (total <= 0) return VPS_OK;
-  maskroi_candidates_kernel<<<vps::cdiv(total, 128), 128, 0, st>>>(rois, cls_score, bbox_pred, nroi, nroi_dev, num_classes,
+  maskroi_candidates_kernel<<<vps::cdiv(total, 128), 128, 0, st>>>(rois, cls_score, bbox_pred, row_stride, nroi, nroi_dev, num_classes,
                                                                  score_thr, img_h, img_w, cand, cand_cls, cand_prob, ncand);
   VPS_CUDA_LAST("maskroi_candidates");
   return VPS_OK;
@@ -436,5 +542,58 @@ extern "C" int vps_track_assign(const float* emb, const float* ref_emb, int k, i
   VPS_CUDA_LAST("track_score");
   track_assign_kernel<<<1, 32, 0, st>>>(match_ids, match_like, k, m, cap, det_obj_ids, mem_src, best_scores, best_ids, new_m);
   VPS_CUDA_LAST("track_assign");
+  return VPS_OK;
+}
+
+extern "C" int vps_rpn_finalize(const float* dets_cat, const int* counts, int nlev, int seg, int cap, float* scores_ws,
+                                float* scores_sorted_ws, int32_t* idx_sorted_ws, void* sort_ws, int64_t sort_ws_bytes,
+                                float* proposals, float* rois, int* total, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = nlev * seg;
+  rpn_concat_scores_kernel<<<vps::cdiv(n, 256), 256, 0, st>>>(dets_cat, counts, nlev, seg, scores_ws, total, cap);
+  VPS_CUDA_LAST("rpn_concat_scores");
+  int rc = vps_sort_desc(scores_ws, scores_sorted_ws, idx_sorted_ws, n, sort_ws, sort_ws_bytes, stream);
+  if (rc != VPS_OK) return rc;
+  rpn_finalize_kernel<<<vps::cdiv(cap, 128), 128, 0, st>>>(dets_cat, idx_sorted_ws, total, cap, proposals, rois);
+  VPS_CUDA_LAST("rpn_finalize");
+  return VPS_OK;
+}
+
+extern "C" int vps_maskroi_finalize(const float* cand_sorted, const int32_t* slot_sorted, const int32_t* cand_cls,
+                                    const int32_t* keep, const int* nkeep, int max_det, int cap, float* det_rois,
+                                    int32_t* cls_idx, float* cls_prob, int* kout, void* stream) {
+  maskroi_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(cand_sorted, slot_sorted, cand_cls, keep, nkeep, max_det, cap,
+                                                             det_rois, cls_idx, cls_prob, kout);
+  VPS_CUDA_LAST("maskroi_finalize");
+  return VPS_OK;
+}
+
+extern "C" int vps_select_class(const vps_tensor* logits, const int32_t* cls_idx, int k, float* out, void* stream) {
+  if (k <= 0) return VPS_OK;
+  VPS_CHECK_ARG(logits->n >= k, "select_class: k");
+  const int64_t total = (int64_t)k * logits->h * logits->w;
+  VPS_DISPATCH_T(logits->dtype, T, (select_class_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                                       vps::tv<const T>(*logits), cls_idx, k, out)));
+  VPS_CUDA_LAST("select_class");
+  return VPS_OK;
+}
+
+extern "C" int vps_track_update(void* mem_feats, const void* det_feats, int dtype, int64_t feat_len, float* mem_boxes,
+                                const float* det_boxes, int32_t* mem_labels, const int32_t* det_labels,
+                                const int32_t* mem_src, int old_m, int cap, const int* new_m_dev, void* stream) {
+  if (cap <= 0) return VPS_OK;
+  dim3 grid(8, cap);
+  VPS_DISPATCH_T(dtype, T, (track_update_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               (T*)mem_feats, (const T*)det_feats, feat_len, mem_boxes, det_boxes, mem_labels, det_labels,
+                               mem_src, old_m, new_m_dev)));
+  VPS_CUDA_LAST("track_update");
+  return VPS_OK;
+}
+
+extern "C" int vps_det_split(const float* det_rois, const int32_t* cls_idx, int cap, float* boxes, int32_t* labels,
+                             void* stream) {
+  if (cap <= 0) return VPS_OK;
+  det_split_kernel<<<vps::cdiv(cap, 128), 128, 0, (cudaStream_t)stream>>>(det_rois, cls_idx, cap, boxes, labels);
+  VPS_CUDA_LAST("det_split");
   return VPS_OK;
 }

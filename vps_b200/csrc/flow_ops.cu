@@ -218,3 +218,62 @@ extern "C" int vps_channelnorm(const vps_tensor* a, const vps_tensor* b, const v
   VPS_CUDA_LAST("channelnorm_kernel");
   return VPS_OK;
 }
+
+// ------------------------------------------------------------------ FlowNet2 input preparation
+// compute_flow + FlowNet2.forward head (panoptic_fusetrack.py:119-121, flow_utils.py:5-10,
+// flownet2.py:135-139): rgb = img*std + mean for both frames, per-channel mean over both frames and all
+// pixels, x = (rgb - rgb_mean) / rgb_max, frames concatenated on channels (img0 -> 0..2, img1 -> 3..5).
+namespace {
+struct F3 { float v[3]; };
+
+__global__ void flownet_sums_kernel(const float* __restrict__ img, const float* __restrict__ ref, int64_t hw, F3 std_, F3 mean_,
+                                    double* __restrict__ sums) {
+  const int c = blockIdx.y;
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    s += (double)(img[c * hw + i] * std_.v[c] + mean_.v[c]);
+    s += (double)(ref[c * hw + i] * std_.v[c] + mean_.v[c]);
+  }
+  __shared__ double sh[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(sums + c, s);
+  }
+}
+
+template <typename T>
+__global__ void flownet_input_kernel(const float* __restrict__ img, const float* __restrict__ ref, int64_t hw, F3 std_,
+                                     F3 mean_, const double* __restrict__ sums, float rgb_max, vps::TV<T> x) {
+  const int64_t total = hw * 6;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c6 = (int)(i % 6);
+    const int64_t pix = i / 6;
+    const int c = c6 % 3;
+    const float* s = c6 < 3 ? img : ref;
+    const float m = (float)(sums[c] / (double)(2 * hw));
+    const float v = (s[c * hw + pix] * std_.v[c] + mean_.v[c] - m) / rgb_max;
+    vps::stf<T>(x.p + pix * x.cs + c6, v);
+  }
+}
+}  // namespace
+
+extern "C" int vps_flownet_input(const float* img_nchw, const float* ref_nchw, int H, int W, const float* std3,
+                                 const float* mean3, float rgb_max, double* sums_ws, const vps_tensor* x, void* stream) {
+  VPS_CHECK_ARG(x->c == 6 && x->h == H && x->w == W && x->n == 1, "flownet_input: x must be [1,H,W,6]");
+  cudaStream_t st = (cudaStream_t)stream;
+  F3 s, m;
+  for (int i = 0; i < 3; ++i) { s.v[i] = std3[i]; m.v[i] = mean3[i]; }
+  const int64_t hw = (int64_t)H * W;
+  cudaMemsetAsync(sums_ws, 0, 3 * sizeof(double), st);
+  dim3 g1(148, 3);
+  flownet_sums_kernel<<<g1, 256, 0, st>>>(img_nchw, ref_nchw, hw, s, m, sums_ws);
+  VPS_CUDA_LAST("flownet_sums");
+  VPS_DISPATCH_T(x->dtype, T, (flownet_input_kernel<T><<<grid_for(hw * 6, 256), 256, 0, st>>>(img_nchw, ref_nchw, hw, s, m,
+                                                                                            sums_ws, rgb_max, vps::tv<T>(*x))));
+  VPS_CUDA_LAST("flownet_input");
+  return VPS_OK;
+}

@@ -33,12 +33,36 @@ class Conv:
         return (x.dtype == torch.bfloat16 and self.cin >= 16 and ops.vt(x).cs % 8 == 0
                 and x.data_ptr() % 16 == 0)
 
+    def _small_cin_tc(self):
+        """bf16 + tiny cin (3..15 channels, first layers): explicit im2col to a K-padded matrix, then the
+        tensor-core kernel runs it as a 1x1 conv.  Weight columns follow vps_im2col: k = (r*kw+s)*cin + ci."""
+        if not hasattr(self, "_pk_cols"):
+            w = self.pk.weight
+            if self.pk.scale is not None:
+                w = w * self.pk.scale.view(-1, 1, 1, 1)
+            co, ci, kh, kw = w.shape
+            kk = kh * kw * ci
+            kpad = (kk + 63) // 64 * 64
+            w2 = torch.zeros(co, kpad, 1, 1, dtype=torch.float32, device=w.device)
+            w2[:, :kk, 0, 0] = w.permute(0, 2, 3, 1).reshape(co, kk)
+            self._pk_cols = PackedConv(w2, self.pk.bias)
+            self._kpad = kpad
+        return self._pk_cols, self._kpad
+
     def __call__(self, x, y=None, act=None, res=None, res_after_act=False, out_scale=1.0, out_dtype=None):
         n, h, w, _ = x.shape
         oh, ow = self.out_hw(h, w)
         if y is None:
             y = empty_nhwc(n, oh, ow, self.cout, out_dtype or x.dtype, x.device)
-        ops.conv2d(x, self.pk, y, stride=self.stride, pad=self.pad, act=self.act if act is None else act,
+        act = self.act if act is None else act
+        if x.dtype == torch.bfloat16 and self.cin < 16 and self.pk.kh * self.pk.kw > 1:
+            pk, kpad = self._small_cin_tc()
+            cols = torch.empty(n, oh, ow, kpad, dtype=torch.bfloat16, device=x.device)
+            ops.im2col(x, cols, self.pk.kh, self.pk.kw, self.stride, self.stride, self.pad, self.pad)
+            ops.conv2d(cols, pk, y, act=act, slope=self.slope, res=res, res_after_act=res_after_act,
+                       out_scale=out_scale, use_tc=True)
+            return y
+        ops.conv2d(x, self.pk, y, stride=self.stride, pad=self.pad, act=act,
                    slope=self.slope, res=res, res_after_act=res_after_act, out_scale=out_scale,
                    use_tc=self.tc_ok(x))
         return y

@@ -131,3 +131,204 @@ def channelnorm(a, out, b=None):
     bb = C.byref(vt(b)) if b is not None else None
     check(lib().vps_channelnorm(C.byref(vt(a)), bb, C.byref(vt(out)), stream()), "channelnorm")
     return out
+
+
+# ------------------------------------------------------------------ layout / pointwise / resampling
+def _bt(t):
+    return C.byref(vt(t))
+
+
+def nchw_to_nhwc(src_nchw, dst):
+    assert src_nchw.dtype == torch.float32 and src_nchw.is_contiguous()
+    check(lib().vps_nchw_to_nhwc(_ptr(src_nchw), _bt(dst), stream()), "nchw_to_nhwc")
+    return dst
+
+
+def nhwc_to_nchw(src, dst_nchw):
+    assert dst_nchw.dtype == torch.float32 and dst_nchw.is_contiguous()
+    check(lib().vps_nhwc_to_nchw(_bt(src), _ptr(dst_nchw), stream()), "nhwc_to_nchw")
+    return dst_nchw
+
+
+def axpby(a, out, alpha=1.0, b=None, beta=0.0):
+    check(lib().vps_axpby(_bt(a), _bt(b) if b is not None else None, _bt(out), C.c_float(alpha), C.c_float(beta),
+                          stream()), "axpby")
+    return out
+
+
+def copy_scale(src, dst, alpha=1.0):
+    return axpby(src, dst, alpha)
+
+
+def resize_bilinear(src, out, mul=1.0):
+    check(lib().vps_resize_bilinear(_bt(src), _bt(out), C.c_float(mul), stream()), "resize_bilinear")
+    return out
+
+
+def resize_nearest(src, out, mul=1.0, accumulate=False):
+    check(lib().vps_resize_nearest(_bt(src), _bt(out), C.c_float(mul), int(accumulate), stream()), "resize_nearest")
+    return out
+
+
+def pool2d(src, out, k, s, p, avg=False):
+    check(lib().vps_pool2d(_bt(src), _bt(out), k, s, p, int(avg), stream()), "pool2d")
+    return out
+
+
+def groupnorm(x, y, gamma, beta, groups, eps=1e-5, relu=False):
+    check(lib().vps_groupnorm(_bt(x), _bt(y), _ptr(gamma), _ptr(beta), groups, C.c_float(eps), int(relu), stream()),
+          "groupnorm")
+    return y
+
+
+def im2col(x, cols, kh, kw, sh, sw, ph, pw):
+    check(lib().vps_im2col(_bt(x), _bt(cols), kh, kw, sh, sw, ph, pw, stream()), "im2col")
+    return cols
+
+
+def flownet_input(img_nchw, ref_nchw, std3, mean3, rgb_max, sums_ws, x):
+    h, w = img_nchw.shape[-2:]
+    s = (C.c_float * 3)(*std3)
+    m = (C.c_float * 3)(*mean3)
+    check(lib().vps_flownet_input(_ptr(img_nchw), _ptr(ref_nchw), h, w, s, m, C.c_float(rgb_max), _ptr(sums_ws), _bt(x),
+                                  stream()), "flownet_input")
+    return x
+
+
+# ------------------------------------------------------------------ BFPTcea / DCN
+def bfp_gather(levels, out):
+    arr = (VpsTensor * len(levels))(*[vt(l) for l in levels])
+    check(lib().vps_bfp_gather(arr, len(levels), _bt(out), stream()), "bfp_gather")
+    return out
+
+
+def bfp_scatter(bsf, inp, out):
+    check(lib().vps_bfp_scatter(_bt(bsf), _bt(inp), _bt(out), stream()), "bfp_scatter")
+    return out
+
+
+def flow_warp(src, flow, out):
+    check(lib().vps_flow_warp(_bt(src), _bt(flow), _bt(out), stream()), "flow_warp")
+    return out
+
+
+def tcea_temporal(fea0, fea1, emb0, emb1, emb_ref, out):
+    check(lib().vps_tcea_temporal(_bt(fea0), _bt(fea1), _bt(emb0), _bt(emb1), _bt(emb_ref), _bt(out), stream()),
+          "tcea_temporal")
+    return out
+
+
+def tcea_combine(fea, att, att_add, out):
+    check(lib().vps_tcea_combine(_bt(fea), _bt(att), _bt(att_add), _bt(out), stream()), "tcea_combine")
+    return out
+
+
+def deform_im2col(x, offset, cols):
+    check(lib().vps_deform_im2col(_bt(x), _bt(offset), _bt(cols), stream()), "deform_im2col")
+    return cols
+
+
+# ------------------------------------------------------------------ detection
+def roi_align(feats, strides, rois, nroi, out, sample_num=2, nroi_dev=None):
+    arr = (VpsTensor * len(feats))(*[vt(f) for f in feats])
+    st = (C.c_int * len(strides))(*strides)
+    check(lib().vps_roi_align(arr, st, len(feats), _ptr(rois), nroi, _ptr(nroi_dev), _bt(out), sample_num, stream()),
+          "roi_align")
+    return out
+
+
+def sort_ws_bytes(n):
+    return n * 24 + (1 << 16)
+
+
+def sort_desc(keys, keys_out, idx_out, n, ws):
+    check(lib().vps_sort_desc(_ptr(keys), _ptr(keys_out), _ptr(idx_out), n, _ptr(ws), C.c_int64(ws.numel() * ws.element_size()),
+                              stream()), "sort_desc")
+
+
+def sigmoid_flat(src, dst):
+    check(lib().vps_sigmoid_flat(_bt(src), _ptr(dst), stream()), "sigmoid_flat")
+    return dst
+
+
+def rpn_decode(scores_sorted, idx_sorted, k, deltas, stride, base_anchors, img_h, img_w, dets):
+    check(lib().vps_rpn_decode(_ptr(scores_sorted), _ptr(idx_sorted), k, _bt(deltas), deltas.shape[1], deltas.shape[2],
+                               stride, _ptr(base_anchors), base_anchors.shape[0], C.c_float(img_h), C.c_float(img_w),
+                               _ptr(dets), stream()), "rpn_decode")
+    return dets
+
+
+def nms_ws_bytes(n):
+    return n * ((n + 63) // 64) * 8
+
+
+def nms(dets, n, thr, keep_idx, nkeep, ws, n_dev=None):
+    check(lib().vps_nms(_ptr(dets), n, _ptr(n_dev), C.c_float(thr), _ptr(keep_idx), _ptr(nkeep), _ptr(ws),
+                        C.c_int64(ws.numel() * ws.element_size()), stream()), "nms")
+
+
+def gather_rows(src, idx, n, width, dst, n_dev=None):
+    check(lib().vps_gather_rows(_ptr(src), _ptr(idx), n, _ptr(n_dev), width, _ptr(dst), stream()), "gather_rows")
+    return dst
+
+
+def maskroi_candidates(rois, cls_score, bbox_pred, nroi, num_classes, thr, img_h, img_w, cand, cand_cls, cand_prob,
+                       ncand, nroi_dev=None):
+    assert cls_score.stride(0) == bbox_pred.stride(0) and cls_score.stride(1) == 1 and bbox_pred.stride(1) == 1
+    check(lib().vps_maskroi_candidates(_ptr(rois), _ptr(cls_score), _ptr(bbox_pred), cls_score.stride(0), nroi,
+                                       _ptr(nroi_dev), num_classes,
+                                       C.c_float(thr), C.c_float(img_h), C.c_float(img_w), _ptr(cand), _ptr(cand_cls),
+                                       _ptr(cand_prob), _ptr(ncand), stream()), "maskroi_candidates")
+
+
+def track_assign(emb, ref_emb, k, m, dim, det_boxes, ref_boxes, det_labels, ref_labels, cls_prob, coeff, cap,
+                 det_obj_ids, match_ids, comp, mem_src, new_m, ws):
+    check(lib().vps_track_assign(_ptr(emb), _ptr(ref_emb), k, m, dim, _ptr(det_boxes), _ptr(ref_boxes), _ptr(det_labels),
+                                 _ptr(ref_labels), _ptr(cls_prob), C.c_float(coeff[0]), C.c_float(coeff[1]),
+                                 C.c_float(coeff[2]), cap, _ptr(det_obj_ids), _ptr(match_ids), _ptr(comp), _ptr(mem_src),
+                                 _ptr(new_m), _ptr(ws), C.c_int64(ws.numel() * ws.element_size()), stream()),
+          "track_assign")
+
+
+# ------------------------------------------------------------------ panoptic fusion
+def mask_removal(boxes, order, k, mask_logit, msize, cls_idx, H, W, frac_thr, occ, num_things, counters, keep_flag,
+                 keep_sorted, nkeep, k_dev=None):
+    check(lib().vps_mask_removal(_ptr(boxes), _ptr(order), k, _ptr(k_dev), _ptr(mask_logit), msize, _ptr(cls_idx), H, W,
+                                 C.c_float(frac_thr), _ptr(occ), num_things, _ptr(counters), _ptr(keep_flag),
+                                 _ptr(keep_sorted), _ptr(nkeep), stream()), "mask_removal")
+
+
+def panoptic_fuse(fcn_score, boxes, cls_idx, mask_logit, msize, keep_sorted, nkeep_dev, kcap, num_stuff, dummy, H, W,
+                  pano_out, sem_out):
+    check(lib().vps_panoptic_fuse(_bt(fcn_score), _ptr(boxes), _ptr(cls_idx), _ptr(mask_logit), msize, _ptr(keep_sorted),
+                                  _ptr(nkeep_dev), kcap, num_stuff, int(dummy), H, W, _ptr(pano_out), _ptr(sem_out),
+                                  stream()), "panoptic_fuse")
+
+
+def rpn_finalize(dets_cat, counts, nlev, seg, cap, scores_ws, scores_sorted_ws, idx_sorted_ws, sort_ws, proposals, rois,
+                 total):
+    check(lib().vps_rpn_finalize(_ptr(dets_cat), _ptr(counts), nlev, seg, cap, _ptr(scores_ws), _ptr(scores_sorted_ws),
+                                 _ptr(idx_sorted_ws), _ptr(sort_ws), C.c_int64(sort_ws.numel() * sort_ws.element_size()),
+                                 _ptr(proposals), _ptr(rois), _ptr(total), stream()), "rpn_finalize")
+
+
+def maskroi_finalize(cand_sorted, slot_sorted, cand_cls, keep, nkeep, max_det, cap, det_rois, cls_idx, cls_prob, kout):
+    check(lib().vps_maskroi_finalize(_ptr(cand_sorted), _ptr(slot_sorted), _ptr(cand_cls), _ptr(keep), _ptr(nkeep), max_det,
+                                     cap, _ptr(det_rois), _ptr(cls_idx), _ptr(cls_prob), _ptr(kout), stream()),
+          "maskroi_finalize")
+
+
+def select_class(logits, cls_idx, k, out):
+    check(lib().vps_select_class(_bt(logits), _ptr(cls_idx), k, _ptr(out), stream()), "select_class")
+    return out
+
+
+def track_update(mem_feats, det_feats, feat_len, mem_boxes, det_boxes, mem_labels, det_labels, mem_src, old_m, cap,
+                 new_m_dev):
+    check(lib().vps_track_update(_ptr(mem_feats), _ptr(det_feats), _DT[mem_feats.dtype], C.c_int64(feat_len),
+                                 _ptr(mem_boxes), _ptr(det_boxes), _ptr(mem_labels), _ptr(det_labels), _ptr(mem_src), old_m,
+                                 cap, _ptr(new_m_dev), stream()), "track_update")
+
+
+def det_split(det_rois, cls_idx, cap, boxes, labels):
+    check(lib().vps_det_split(_ptr(det_rois), _ptr(cls_idx), cap, _ptr(boxes), _ptr(labels), stream()), "det_split")
