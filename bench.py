@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- FuseTrack frame pairs / second on synthetic 1024x2048 pairs (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU, clips sharded)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the oracle port on the host CPU cores
+
+One step = one `simple_test` call = one frame pair -> one panoptic frame.  Prints ONE JSON line (rank 0).
+  value      : pairs/s, inputs already resident in HBM, device-timed (CUDA events), max over ranks, summed over ranks
+  e2e        : same through the public detector call with HOST (pinned) frames: H2D of both frames and D2H of the
+               label maps inside the timed region
+  roofline   : the dominant kernel (tcgen05 implicit-GEMM conv, all launches of a step): algorithmic conv FLOPs /
+               summed kernel time, against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline: the oracle (CPU port of the reference math) on a bounded sample, host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H_FULL, W_FULL = 1024, 2048
+METRIC = "FuseTrack frame pairs/s on synthetic 1024x2048 pairs"
+# algorithmic dense work per pair at 1024x2048, GFLOP
+GFLOP_R50FPN_PAIR = 1158.4
+GFLOP_ALL_PAIR = 5017.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu=0):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def synth_pairs(n, H, W, seed=0):
+    """n distinct synthetic (img, ref) pairs, post-Normalize statistics, ref = shifted img + noise."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(n):
+        img = torch.randn(1, 3, H, W, generator=g)
+        ref = torch.roll(img, shifts=(2 + i % 3, 3 + i % 5), dims=(2, 3)) + 0.05 * torch.randn(1, 3, H, W, generator=g)
+        out.append((img.contiguous(), ref.contiguous()))
+    return out
+
+
+def meta(iid, H, W):
+    return dict(filename="synthetic_city_%06d.png" % iid, iid=iid, img_shape=(H, W, 3), pad_shape=(H, W, 3),
+                ori_shape=(H, W, 3), scale_factor=1.0)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def oracle_model():
+    from oracle.model import PanopticFuseTrack as Oracle
+    from vps_b200.synth import make_weights
+    m = Oracle()
+    make_weights(m, "C", 0)
+    return m
+
+
+def time_oracle(model, H, W, reps, threads):
+    torch.set_num_threads(threads)
+    pairs = synth_pairs(1, H, W, seed=3)
+    times = []
+    for r in range(reps):
+        t = time.perf_counter()
+        model.simple_test(pairs[0][0], dict(iid=10001 + r, img_shape=(H, W, 3)), pairs[0][1])
+        times.append(time.perf_counter() - t)
+    return times
+
+
+def cpu_baseline(budget_s=30.0):
+    """Oracle on the host cores on a bounded sample: one frame pair at the largest size (1/16, 1/4 or full area)
+    whose predicted time fits the budget; scaled to 1024x2048-equivalent pairs/s by the area ratio (the dense
+    work is linear in pixels)."""
+    cores = os.cpu_count() or 1
+    m = oracle_model()
+    t_small = min(time_oracle(m, 256, 512, 2, cores))            # 1/16 area (first call includes warm-up)
+    size, frac, t = (256, 512), 1.0 / 16, t_small
+    if t_small * 4 * 1.2 <= budget_s:
+        t4 = time_oracle(m, 512, 1024, 1, cores)[0]
+        size, frac, t = (512, 1024), 0.25, t4
+        if t4 * 4 * 1.2 <= budget_s:
+            t = time_oracle(m, 1024, 2048, 1, cores)[0]
+            size, frac = (1024, 2048), 1.0
+    return {"value": frac / t, "unit": "pairs/s (1024x2048-equivalent)", "cores": cores, "kind": "port",
+            "sample": "oracle simple_test, 1 pair at %dx%d (%.3g of the 1024x2048 area) in %.2fs, scaled by area; fp32, torch CPU ops"
+                      % (size[0], size[1], frac, t)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own math on the host CPU.  The reference cannot execute on this stack
+    (mmcv 0.2.14 + THC extensions, hard .cuda() calls), so this is the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    m = oracle_model()
+    Hs, Ws = 256, 512                                # each step = 1/16 of a 1024x2048 pair's area
+    frac = (Hs * Ws) / float(H_FULL * W_FULL)
+    times = time_oracle(m, Hs, Ws, args.warmup + args.steps, cores)[args.warmup:]
+    t = float(np.mean(times))
+    v = frac / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / frac, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FuseTrack inference, synthetic 2-frame 1024x2048 pair, random-init (synthetic set C) weights",
+                       "sample": "each step = one 256x512 pair (1/16 area) on CPU, scaled by area"},
+            "cpu_baseline": {"value": v, "unit": "pairs/s (1024x2048-equivalent)", "cores": cores, "kind": "port",
+                             "sample": "oracle simple_test, %d steps of one 256x512 pair, scaled by area" % args.steps},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_product(precision, device):
+    from vps_b200 import ConfigDict, build_detector, fusetrack_cfg
+    from vps_b200.synth import make_weights
+    c = fusetrack_cfg()
+    det = build_detector(ConfigDict(c["model"]), train_cfg=None, test_cfg=ConfigDict(c["test_cfg"]))
+    make_weights(det, "C", 0)
+    det.precision = precision
+    det = det.to(device)
+    det.prepare()
+    return det
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from vps_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W = args.height, args.width
+    det = build_product(args.precision, dev)
+    NPAIR = 4                                        # 4 distinct pairs = 201 MB of fp32 frames (> 126 MB L2)
+    host = [(a.pin_memory(), b.pin_memory()) for a, b in synth_pairs(NPAIR, H, W, seed=100 + rank)]
+    devp = [(a.to(dev), b.to(dev)) for a, b in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    CLIP = 30                                        # Cityscapes-VPS clip length: tracker memory resets every 30 frames
+
+    def step(i, from_host):
+        iid = 10000 * (1 + rank) + 1 + (i % CLIP)
+        if from_host:
+            a = host[i % NPAIR][0].to(dev, non_blocking=True)
+            b = host[i % NPAIR][1].to(dev, non_blocking=True)
+        else:
+            a, b = devp[i % NPAIR]
+        r = det.simple_test(a, [meta(iid, H, W)], ref_img=[b])
+        if from_host:
+            pano = r[2]["panoptic_outputs"].to("cpu", non_blocking=True)
+            sem = r[2]["fcn_outputs"].to("cpu", non_blocking=True)
+            return pano, sem
+        return r
+
+    def timed(nsteps, from_host, offset):
+        evs = []
+        for i in range(nsteps):
+            flush.fill_(i & 0xff)                    # L2 flush between timed iterations (outside the timed span)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step(offset + i, from_host)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in evs]
+
+    for i in range(args.warmup):
+        step(i, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launch_count()
+    ms = timed(args.steps, False, args.warmup)
+    launches = ops.launch_count() - l0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_e2e = timed(args.steps, True, args.warmup + args.steps)
+    sampler.stop_flag = True
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = [float(v) / 1e3 for v in tot.tolist()]
+    value = world * args.steps / t_dev
+    e2e = world * args.steps / t_e2e
+
+    # ---- per-kernel attribution (separate instrumented steps, not part of the timed region)
+    roof, breakdown = None, None
+    if rank == 0:
+        ops.PROFILE = []
+        for i in range(2):
+            step(args.warmup + 2 * args.steps + i, False)
+        torch.cuda.synchronize()
+        rec, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for name, s, e, fl, tag in rec:
+            a = agg.setdefault(name, [0.0, 0.0, 0])
+            a[0] += s.elapsed_time(e); a[1] += fl; a[2] += 1
+        tc_ms, tc_fl, tc_n = agg.get("vps_conv2d_tc", [0.0, 0.0, 0])
+        pk = peaks()
+        if tc_ms > 0:
+            ach = tc_fl / (tc_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "conv_igemm_tc_kernel (all %d launches of a step)" % (tc_n // 2),
+                    "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
+                    "peak_source": pk["src"] + " bf16_tflops_sustained",
+                    "flops_per_step": tc_fl / 2, "ms_per_step": tc_ms / 2}
+        total_ms = sum(a[0] for a in agg.values())
+        breakdown = {k: {"ms_per_step": round(a[0] / 2, 3), "share": round(a[0] / total_ms, 4), "calls": a[2] // 2}
+                     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+
+    if rank == 0:
+        clocks = sampler.summary()
+        bytes_in = 2 * 3 * H * W * 4
+        bytes_out = 2 * H * W * 8
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "FuseTrack inference, synthetic 2-frame %dx%d pair, random-init (synthetic set C) weights, "
+                                       "1 clip stream per GPU" % (H, W),
+                           "parallelism": "clip-sharded replicas x%d, no data-path collective" % world,
+                           "l2": "256 MiB L2 flush between timed steps + 4 rotating input pairs (201 MB)",
+                           "precision_note": "bf16 operands / fp32 accumulate on tcgen05; fp32 parity mode via --precision fp32"},
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "conv_flop_frac_whole_path": GFLOP_ALL_PAIR * (H * W) / float(H_FULL * W_FULL) * 1e9 * args.steps / t_dev / 1e12 / peaks()["tf_sus"]}
+        if roof:
+            line["roofline"] = roof
+        if breakdown:
+            line["breakdown"] = breakdown
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--height", type=int, default=H_FULL)
+    ap.add_argument("--width", type=int, default=W_FULL)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -8,101 +8,9 @@
   "C": B + detection forcing: bbox_head.fc_cls scaled up / fc_reg scaled down so that >= a few dozen
        RoIs pass the 0.6 threshold and the mask / tracking / fusion stages see real instances.
 """
-import math
-
 import torch
-import torch.nn as nn
 
-
-def _kaiming_uniform(w, gain=1.0):
-    fan_in = w[0].numel()
-    bound = gain * math.sqrt(3.0 / fan_in)
-    w.uniform_(-bound, bound)
-
-
-@torch.no_grad()
-def init_weights(model, kind="C", seed=0):
-    g = torch.Generator().manual_seed(seed)
-
-    def U(t, a, b):
-        t.copy_(torch.rand(t.shape, generator=g) * (b - a) + a)
-
-    def N(t, mean, std):
-        t.copy_(torch.randn(t.shape, generator=g) * std + mean)
-
-    if kind == "A":
-        for name, m in model.named_modules():
-            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)):
-                if name.startswith("flownet2"):
-                    fan_in = m.weight[0].numel() if not isinstance(m, nn.ConvTranspose2d) else m.weight.shape[0] * m.weight[0, 0].numel()
-                    fan_out = m.weight.shape[0] * m.weight[0, 0].numel() if not isinstance(m, nn.ConvTranspose2d) else m.weight[0].numel()
-                    b = math.sqrt(6.0 / (fan_in + fan_out))
-                    U(m.weight, -b, b)
-                    if m.bias is not None:
-                        U(m.bias, 0, 1)
-                elif name.startswith("backbone"):
-                    fan_out = m.weight.shape[0] * m.weight[0, 0].numel()
-                    N(m.weight, 0, math.sqrt(2.0 / fan_out))
-                elif name.startswith(("rpn_head", "track_head")):
-                    N(m.weight, 0, 0.01); m.bias.zero_()
-                elif name == "bbox_head.fc_cls":
-                    N(m.weight, 0, 0.01); m.bias.zero_()
-                elif name == "bbox_head.fc_reg":
-                    N(m.weight, 0, 0.001); m.bias.zero_()
-                else:   # xavier uniform (FPN, BFPTcea, UPSNetFPN, shared fcs); kaiming for mask head is close enough
-                    fan_in = m.weight[0].numel()
-                    fan_out = m.weight.shape[0] * (m.weight[0, 0].numel() if m.weight.dim() > 2 else 1)
-                    b = math.sqrt(6.0 / (fan_in + fan_out))
-                    U(m.weight, -b, b)
-                    if m.bias is not None:
-                        m.bias.zero_()
-            elif isinstance(m, nn.BatchNorm2d):
-                m.weight.fill_(1); m.bias.zero_(); m.running_mean.zero_(); m.running_var.fill_(1)
-                if name.endswith("bn3"):
-                    m.weight.zero_()
-        return model
-
-    for name, m in model.named_modules():
-        if isinstance(m, (nn.Conv2d, nn.Linear)):
-            _g = 1.4 if not name.startswith("flownet2") else 1.0
-            fan_in = m.weight[0].numel()
-            bound = _g * math.sqrt(3.0 / fan_in)
-            U(m.weight, -bound, bound)
-            if m.bias is not None:
-                N(m.bias, 0, 0.05)
-        elif isinstance(m, nn.ConvTranspose2d):
-            fan_in = m.weight.shape[0] * m.weight[0, 0].numel() / 4.0   # stride-2: ~1/4 of taps hit each output
-            bound = math.sqrt(3.0 / fan_in)
-            U(m.weight, -bound, bound)
-            if m.bias is not None:
-                N(m.bias, 0, 0.05)
-        elif isinstance(m, nn.BatchNorm2d):
-            U(m.weight, 0.5, 1.5); N(m.bias, 0, 0.1); N(m.running_mean, 0, 0.1); U(m.running_var, 0.5, 1.5)
-            if name.endswith("bn3"):
-                m.weight.mul_(0.5)      # keep the residual trunk from blowing up over 16 blocks
-        elif isinstance(m, nn.GroupNorm):
-            U(m.weight, 0.5, 1.5); N(m.bias, 0, 0.1)
-        elif m.__class__.__name__ == "DeformConv":
-            fan_in = m.weight[0].numel()
-            bound = 1.4 * math.sqrt(3.0 / fan_in)
-            U(m.weight, -bound, bound)
-    # DCN offsets: moderate non-zero offsets (a few pixels)
-    for name, m in model.named_modules():
-        if name.endswith("conv_offset"):
-            N(m.weight, 0, 0.02); N(m.bias, 0, 0.5)
-    # FlowNet2 predicts flows through 5 stacked nets; keep predictions O(1 px)
-    for name, m in model.named_modules():
-        if name.startswith("flownet2") and "predict_flow" in name:
-            m.weight.mul_(0.2)
-    # RPN: spread objectness and keep deltas moderate
-    model.rpn_head.rpn_cls.weight.mul_(2.0)
-    model.rpn_head.rpn_reg.weight.mul_(0.3)
-    if kind == "C":
-        model.bbox_head.fc_cls.weight.mul_(6.0)
-        model.bbox_head.fc_cls.bias[0] -= 1.0
-        model.bbox_head.fc_reg.weight.mul_(0.3)
-        model.mask_head.conv_logits.weight.mul_(3.0)
-    return model
+from vps_b200.synth import init_weights  # noqa: F401  (shared, model-agnostic parameter initialiser)
 
 
 @torch.no_grad()

@@ -107,3 +107,17 @@ def test_no_cpu_fallback():
     src = "".join(open(os.path.join(ROOT, "vps_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "vps_b200"))
                   if f.endswith(".py"))
     assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_synth_table_matches_oracle_calibration():
+    """vps_b200.synth.make_weights (table-driven) reproduces oracle.weights.make_model (measured calibration)."""
+    from oracle.weights import make_model
+    from vps_b200 import ConfigDict, build_detector, fusetrack_cfg
+    from vps_b200.synth import make_weights
+    c = fusetrack_cfg()
+    det = build_detector(ConfigDict(c["model"]), train_cfg=None, test_cfg=ConfigDict(c["test_cfg"]))
+    make_weights(det, "C", 0)
+    a, b = det.state_dict(), make_model("C", 0).state_dict()
+    for k in a:
+        tol = 2e-5 * max(1.0, float(b[k].abs().max()))
+        assert float((a[k].float() - b[k].float()).abs().max()) <= tol, k

@@ -15,6 +15,35 @@ from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, VPS_BF16, VPS_F32
 
 _DT = {torch.float32: VPS_F32, torch.bfloat16: VPS_BF16}
 
+# ---- optional per-call device timing (bench.py / profiling only; off on the normal path) -----------------
+PROFILE = None        # set to a list to collect [c_function, start_event, end_event, flops, tag] per C-ABI call
+_NOTE = {"flops": 0, "tag": ""}
+_real_lib = lib
+
+
+class _ProfLib(object):
+    def __getattr__(self, name):
+        f = getattr(_real_lib(), name)
+        if PROFILE is None or not name.startswith("vps_") or name in ("vps_last_error", "vps_launch_count", "vps_packed_tc_bytes"):
+            return f
+
+        def w(*a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = f(*a)
+            e.record()
+            PROFILE.append([name, s, e, _NOTE["flops"], _NOTE["tag"]])
+            _NOTE["flops"], _NOTE["tag"] = 0, ""
+            return r
+        return w
+
+
+_plib = _ProfLib()
+
+
+def lib():  # noqa: F811  (shadows the import: every wrapper below goes through the profiling proxy)
+    return _plib
+
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -106,6 +135,9 @@ def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_aft
     a.bias = pw.bias.data_ptr() if pw.bias is not None else None
     if use_tc is None:
         use_tc = x.dtype == torch.bfloat16
+    if PROFILE is not None:
+        _NOTE["flops"] = 2 * x.shape[0] * oh * ow * pw.cout * pw.cin * kh * kw
+        _NOTE["tag"] = "%dx%d s%d %d->%d @%dx%d" % (kh, kw, sh, pw.cin, pw.cout, oh, ow)
     if use_tc:
         a.w = (w_override if w_override is not None else pw.tc()).data_ptr()
         check(lib().vps_conv2d_tc(C.byref(a), stream()), "conv2d_tc")
