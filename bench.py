@@ -240,6 +240,11 @@ def run_gpu_arm(args):
             step(args.warmup + 2 * args.steps + i, False)
         torch.cuda.synchronize()
         rec, ops.PROFILE = ops.PROFILE, None
+        if args.profile_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)) or ".", exist_ok=True)
+            with open(args.profile_out, "w") as f:
+                for name, s, e, fl, tag in rec[len(rec) // 2:]:
+                    f.write(json.dumps({"fn": name, "ms": s.elapsed_time(e), "flops": fl, "tag": tag}) + "\n")
         agg = {}
         for name, s, e, fl, tag in rec:
             a = agg.setdefault(name, [0.0, 0.0, 0])
@@ -293,6 +298,7 @@ def main():
     ap.add_argument("--height", type=int, default=H_FULL)
     ap.add_argument("--width", type=int, default=W_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write per-call device timings of one instrumented step (JSON lines)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

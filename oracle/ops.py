@@ -230,8 +230,15 @@ def roi_align(feat, rois, out_size, spatial_scale, sample_num):
             xc = torch.where(xtop, x_low.float(), xc)
             ly, lx = yc - y_low.float(), xc - x_low.float()
             hy, hx = 1.0 - ly, 1.0 - lx
-            fb = f[bi]  # [n,C,H,W]
-            idx = lambda yi, xi: fb.view(n, C, H * W).gather(2, (yi * W + xi).view(n, 1, ph * pw).expand(n, C, ph * pw)).view(n, C, ph, pw)
+            def idx(yi, xi):
+                # gather f[b, :, yi, xi] for every (roi, ph, pw) without materialising f[bi]
+                out_ = torch.empty((n, C, ph, pw), dtype=torch.float32)
+                lin = yi * W + xi
+                for b in torch.unique(bi).tolist():
+                    sel = (bi == b).nonzero(as_tuple=True)[0]
+                    fb = f[b].reshape(C, H * W)
+                    out_[sel] = fb[:, lin[sel].reshape(-1)].reshape(C, sel.numel(), ph, pw).permute(1, 0, 2, 3)
+                return out_
             lt, rt, lb, rb = idx(y_low, x_low), idx(y_low, x_high), idx(y_high, x_low), idx(y_high, x_high)
             w1, w2, w3, w4 = (hy * hx)[:, None], (hy * lx)[:, None], (ly * hx)[:, None], (ly * lx)[:, None]
             val = w1 * lt + w2 * rt + w3 * lb + w4 * rb

@@ -83,3 +83,60 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 }
 
 }  // namespace vps
+
+// ---- vectorised channel access: V consecutive channels per thread (V = 16 bytes / sizeof(T), or 1) ----
+namespace vps {
+template <typename T> struct VecW;
+template <> struct VecW<float> { static constexpr int value = 4; };
+template <> struct VecW<__nv_bfloat16> { static constexpr int value = 8; };
+
+template <typename T, int V>
+__device__ __forceinline__ void ldv(const T* p, float (&v)[V]) {
+  if constexpr (V == 1) {
+    v[0] = ldf<T>(p);
+  } else if constexpr (sizeof(T) == 4) {
+    static_assert(V == 4, "fp32 vector width");
+    const float4 f = *reinterpret_cast<const float4*>(p);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  } else {
+    static_assert(V == 8, "bf16 vector width");
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(b2[j]);
+      v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv(T* p, const float (&v)[V]) {
+  if constexpr (V == 1) {
+    stf<T>(p, v[0]);
+  } else if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+}
+// can tensor t be accessed with V-wide vectors of its dtype over its first `c` channels?
+static inline bool vec_ok(const vps_tensor& t, int c) {
+  const int V = t.dtype == VPS_F32 ? 4 : 8;
+  return c % V == 0 && t.cs % V == 0 && ((uintptr_t)t.ptr & 15) == 0;
+}
+// launch geometry of the (x*chunks, y, n) pixel grid
+static inline dim3 pix_grid(int w, int chunks, int h, int n, int threads = 256) {
+  return dim3((unsigned)cdiv((int64_t)w * chunks, threads), (unsigned)h, (unsigned)n);
+}
+}  // namespace vps
+
+// per-thread coordinates for kernels launched with vps::pix_grid: V channels starting at `c`, pixel (n,y,x)
+#define VPS_PIX_COORDS(OUT, V, c_, x_, y_, n_)                           \
+  const int chunks__ = (OUT).c / (V);                                    \
+  const int t__ = blockIdx.x * blockDim.x + threadIdx.x;                 \
+  if (t__ >= (OUT).w * chunks__) return;                                 \
+  const int c_ = (t__ % chunks__) * (V), x_ = t__ / chunks__, y_ = blockIdx.y, n_ = blockIdx.z

@@ -27,7 +27,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                      // 2 per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 
@@ -43,7 +44,7 @@ struct ConvTcParams {
   int y_h, y_w, y_cs, y_dtype, y_vec;
   int oy_mul, oy_off, ox_mul, ox_off;
   const void* res;
-  int res_cs, res_dtype, res_after_act;
+  int res_cs, res_dtype, res_after_act, res_vec;
   const float* bias;
   int cout;
   int act;
@@ -142,7 +143,150 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- epilogue math for one 32-column chunk of one pixel
+template <int ACT>
+__device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t (&r)[32], int64_t pix, int n0) {
+  const int nv = min(32, p.cout - n0);
+  const bool full = nv == 32;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias) {
+    if (full) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);   // n0 % 32 == 0, bias 16-byte aligned (host check)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(bp + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nv) v[j] += __ldg(p.bias + n0 + j);
+    }
+  }
+  const bool has_res = p.res != nullptr;
+  // residual added in place (no second register array); `pass` 0 = before the activation, 1 = after it
+  auto add_res = [&]() {
+    const int64_t ro = pix * p.res_cs + n0;
+    if (p.res_dtype == VPS_BF16) {
+      const __nv_bfloat16* rp = (const __nv_bfloat16*)p.res + ro;
+      if (full && p.res_vec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(rp + 8 * j);
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(b2[t]);
+            v[8 * j + 2 * t] += f.x; v[8 * j + 2 * t + 1] += f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nv) v[j] += __bfloat162float(rp[j]);
+      }
+    } else {
+      const float* rp = (const float*)p.res + ro;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nv) v[j] += rp[j];
+    }
+  };
+  if (has_res && !p.res_after_act) add_res();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float t = v[j];
+    if (ACT == VPS_ACT_RELU) t = fmaxf(t, 0.f);
+    else if (ACT == VPS_ACT_LRELU) t = t > 0.f ? t : t * p.slope;
+    else if (ACT == VPS_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+    v[j] = t * p.out_scale;
+  }
+  if (has_res && p.res_after_act) add_res();
+  const int64_t yo = pix * p.y_cs + n0;
+  if (p.y_dtype == VPS_BF16) {
+    __nv_bfloat16* yp = (__nv_bfloat16*)p.y + yo;
+    if (p.y_vec && full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        pk.x = *(uint32_t*)&b0; pk.y = *(uint32_t*)&b1; pk.z = *(uint32_t*)&b2; pk.w = *(uint32_t*)&b3;
+        *(uint4*)(yp + j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nv) yp[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* yp = (float*)p.y + yo;
+    if (p.y_vec && full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *(float4*)(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nv) yp[j] = v[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- epilogue role (warps 2..9)
+// warp -> TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter take alternate
+// 32-column chunks.  Two register sets: the next chunk's tcgen05.ld is in flight while the current one is processed.
+template <int ACT>
+__device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              int warp, int lane) {
+  const int q = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int row = q * 32 + lane;
+  const int ty_in = row / p.tw, tx_in = row - ty_in * p.tw;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int n_idx = tile % p.n_tiles_n;
+    const int m_idx = tile / p.n_tiles_n;
+    const int img = m_idx / tiles_per_img;
+    const int rem = m_idx - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int oy = ty * p.th + ty_in, ox = tx * p.tw + tx_in;
+    const bool valid = (oy < p.oh) && (ox < p.ow);
+    const int64_t pix = ((int64_t)img * p.y_h + (oy * p.oy_mul + p.oy_off)) * p.y_w + (ox * p.ox_mul + p.ox_off);
+    const int nbase = n_idx * p.block_n;
+
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+    uint32_t ra[32], rb[32];
+    int c0 = half * 32;
+    if (c0 < p.block_n) tmem_ld32(t_row + (uint32_t)c0, ra);
+    while (c0 < p.block_n) {
+      tmem_ld_wait();
+      const int c1 = c0 + 64;
+      if (c1 < p.block_n) tmem_ld32(t_row + (uint32_t)c1, rb);
+      if (valid && nbase + c0 < p.cout) epi_chunk<ACT>(p, ra, pix, nbase + c0);
+      if (c1 >= p.block_n) break;
+      tmem_ld_wait();
+      const int c2 = c1 + 64;
+      if (c2 < p.block_n) tmem_ld32(t_row + (uint32_t)c2, ra);
+      if (valid && nbase + c1 < p.cout) epi_chunk<ACT>(p, rb, pix, nbase + c1);
+      c0 = c2;
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(tempty0 + 8u * acc);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
 }
 
 // ---------------------------------------------------------------- kernel
@@ -171,7 +315,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -256,100 +400,12 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int ty_in = row / p.tw, tx_in = row - ty_in * p.tw;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_idx = tile % p.n_tiles_n;
-      const int m_idx = tile / p.n_tiles_n;
-      const int img = m_idx / tiles_per_img;
-      const int rem = m_idx - img * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int oy = ty * p.th + ty_in, ox = tx * p.tw + tx_in;
-      const bool valid = (oy < p.oh) && (ox < p.ow);
-      const int64_t pix =
-          ((int64_t)img * p.y_h + (oy * p.oy_mul + p.oy_off)) * p.y_w + (ox * p.ox_mul + p.ox_off);
-
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)c0, r);
-        const int n0 = n_idx * p.block_n + c0;
-        if (valid && n0 < p.cout) {
-          const int nv = min(32, p.cout - n0);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) v[j] += __ldg(p.bias + n0 + j);
-          }
-          float rs[32];
-          const bool has_res = p.res != nullptr;
-          if (has_res) {
-            const int64_t ro = pix * p.res_cs + n0;
-            if (p.res_dtype == VPS_BF16) {
-              const __nv_bfloat16* rp = (const __nv_bfloat16*)p.res + ro;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) rs[j] = (j < nv) ? __bfloat162float(rp[j]) : 0.f;
-            } else {
-              const float* rp = (const float*)p.res + ro;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) rs[j] = (j < nv) ? rp[j] : 0.f;
-            }
-            if (!p.res_after_act) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += rs[j];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = vps::apply_act(v[j], p.act, p.slope) * p.out_scale;
-          if (has_res && p.res_after_act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += rs[j];
-          }
-          const int64_t yo = pix * p.y_cs + n0;
-          if (p.y_dtype == VPS_BF16) {
-            __nv_bfloat16* yp = (__nv_bfloat16*)p.y + yo;
-            if (p.y_vec && nv == 32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *(uint32_t*)&b0; pk.y = *(uint32_t*)&b1; pk.z = *(uint32_t*)&b2; pk.w = *(uint32_t*)&b3;
-                *(uint4*)(yp + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) yp[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else {
-            float* yp = (float*)p.y + yo;
-            if (p.y_vec && nv == 32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *(float4*)(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) yp[j] = v[j];
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+    // ===================== epilogue (warps 2..9) =====================
+    switch (p.act) {
+      case VPS_ACT_RELU: epilogue_loop<VPS_ACT_RELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane); break;
+      case VPS_ACT_LRELU: epilogue_loop<VPS_ACT_LRELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane); break;
+      case VPS_ACT_SIGMOID: epilogue_loop<VPS_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane); break;
+      default: epilogue_loop<VPS_ACT_NONE>(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane); break;
     }
   }
 
@@ -458,6 +514,13 @@ extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) {
     block_n = 256;
     while (cout_pad % block_n) block_n -= 16;
   }
+  // small problems: shrink the N tile until the persistent grid is filled (more, smaller tiles; A re-reads hit L2)
+  {
+    const int64_t m_tiles = (int64_t)a->x.n * p.tiles_y * p.tiles_x;
+    while (m_tiles * (cout_pad / block_n) < g_num_sms && block_n >= 64 && (block_n / 2) % 16 == 0 &&
+           cout_pad % (block_n / 2) == 0)
+      block_n /= 2;
+  }
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
   p.kh = a->kh; p.kw = a->kw; p.sh = a->sh; p.sw = a->sw; p.ph = a->ph; p.pw = a->pw;
   p.cin_chunks = cin_pad / 64;
@@ -471,6 +534,8 @@ extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) {
   p.y_vec = (((uintptr_t)a->y.ptr & 15) == 0) && ((a->y.cs * esz) % 16 == 0);
   p.oy_mul = a->oy_mul; p.oy_off = a->oy_off; p.ox_mul = a->ox_mul; p.ox_off = a->ox_off;
   p.res = a->res.ptr; p.res_cs = a->res.cs; p.res_dtype = a->res.dtype; p.res_after_act = a->res_after_act;
+  p.res_vec = a->res.ptr && (((uintptr_t)a->res.ptr & 15) == 0) && (a->res.cs % 8 == 0);
+  VPS_CHECK_ARG(!a->bias || ((uintptr_t)a->bias & 15) == 0, "conv2d_tc: bias must be 16-byte aligned");
   p.bias = a->bias; p.cout = a->cout; p.act = a->act; p.slope = a->slope; p.out_scale = a->out_scale;
   VPS_CHECK_ARG((a->oh - 1) * a->oy_mul + a->oy_off < a->y.h && (a->ow - 1) * a->ox_mul + a->ox_off < a->y.w,
                 "conv2d_tc: output mapping out of range");

@@ -24,11 +24,11 @@ struct Feats {
   int n;
 };
 
-// roi_align_kernel.cu:16-45
-template <typename T>
-__device__ __forceinline__ float bilinear_legacy(const vps::TV<const T>& f, int b, int c, float y, float x) {
+// roi_align_kernel.cu:16-45, V channels at once: acc += bilinear(feature, y, x)
+template <typename T, int V>
+__device__ __forceinline__ void bilinear_legacy_acc(const vps::TV<const T>& f, int b, int c, float y, float x, float (&acc)[V]) {
   const int H = f.h, W = f.w;
-  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) return 0.f;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) return;
   if (y <= 0.f) y = 0.f;
   if (x <= 0.f) x = 0.f;
   int y_low = (int)y, x_low = (int)x, y_high, x_high;
@@ -36,28 +36,28 @@ __device__ __forceinline__ float bilinear_legacy(const vps::TV<const T>& f, int 
   if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else { x_high = x_low + 1; }
   const float ly = y - (float)y_low, lx = x - (float)x_low;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const float lt = vps::ldf<T>(f.p + f.off(b, y_low, x_low) + c);
-  const float rt = vps::ldf<T>(f.p + f.off(b, y_low, x_high) + c);
-  const float lb = vps::ldf<T>(f.p + f.off(b, y_high, x_low) + c);
-  const float rb = vps::ldf<T>(f.p + f.off(b, y_high, x_high) + c);
   const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-  return w1 * lt + w2 * rt + w3 * lb + w4 * rb;
+  float lt[V], rt[V], lb[V], rb[V];
+  vps::ldv<T, V>(f.p + f.off(b, y_low, x_low) + c, lt);
+  vps::ldv<T, V>(f.p + f.off(b, y_low, x_high) + c, rt);
+  vps::ldv<T, V>(f.p + f.off(b, y_high, x_low) + c, lb);
+  vps::ldv<T, V>(f.p + f.off(b, y_high, x_high) + c, rb);
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] += w1 * lt[j] + w2 * rt[j] + w3 * lb[j] + w4 * rb[j];
 }
 
 // ROIAlignForward (roi_align_kernel.cu:64-128) + map_roi_levels (single_level.py:54-73), one launch for all levels.
-template <typename T>
+// grid: (pw * channel-chunks, ph, roi)
+template <typename T, int V>
 __global__ void roi_align_kernel(Feats<T> fs, const float* __restrict__ rois, int nroi, const int* __restrict__ nroi_dev,
-                                 vps::TV<T> out, int ps, int sample_num, int64_t total) {
+                                 vps::TV<T> out, int ps, int sample_num) {
+  VPS_PIX_COORDS(out, V, c, pw, ph, r);
   const int nvalid = nroi_dev ? min(*nroi_dev, nroi) : nroi;
-  const int C = out.c;
-  GRID_STRIDE(i, total) {
-    const int c = (int)(i % C);
-    int64_t t = i / C;
-    const int pw = (int)(t % ps); t /= ps;
-    const int ph = (int)(t % ps);
-    const int r = (int)(t / ps);
-    T* op = out.p + out.off(r, ph, pw) + c;
-    if (r >= nvalid) { vps::stf<T>(op, 0.f); continue; }
+  T* op = out.p + out.off(r, ph, pw) + c;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  if (r < nvalid) {
     const float* roi = rois + (int64_t)r * 5;
     const int b = (int)roi[0];
     const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
@@ -68,16 +68,23 @@ __global__ void roi_align_kernel(Feats<T> fs, const float* __restrict__ rois, in
     const float rsw = x1 * ss, rsh = y1 * ss, rew = (x2 + 1.f) * ss, reh = (y2 + 1.f) * ss;
     const float rw = fmaxf(rew - rsw, 0.f), rh = fmaxf(reh - rsh, 0.f);
     const float bh = rh / (float)ps, bw = rw / (float)ps;
-    float acc = 0.f;
     for (int iy = 0; iy < sample_num; ++iy) {
       const float y = rsh + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)sample_num;
       for (int ix = 0; ix < sample_num; ++ix) {
         const float x = rsw + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)sample_num;
-        acc += bilinear_legacy<T>(fs.l[lvl], b, c, y, x);
+        // level is warp-divergent at most across RoIs (blockIdx.z), never inside a block
+        switch (lvl) {
+          case 0: bilinear_legacy_acc<T, V>(fs.l[0], b, c, y, x, acc); break;
+          case 1: bilinear_legacy_acc<T, V>(fs.l[1], b, c, y, x, acc); break;
+          case 2: bilinear_legacy_acc<T, V>(fs.l[2], b, c, y, x, acc); break;
+          default: bilinear_legacy_acc<T, V>(fs.l[3], b, c, y, x, acc); break;
+        }
       }
     }
-    vps::stf<T>(op, acc / (float)(sample_num * sample_num));
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] /= (float)(sample_num * sample_num);
   }
+  vps::stv<T, V>(op, acc);
 }
 
 // ------------------------------------------------------------------ RPN decode (rpn_head.py:73-85, transforms.py:34-68)
@@ -436,19 +443,25 @@ __global__ void det_split_kernel(const float* __restrict__ det_rois, const int32
 extern "C" int vps_roi_align(const vps_tensor* feats, const int* strides, int nlev, const float* rois, int nroi,
                              const int* nroi_dev, const vps_tensor* out, int sample_num, void* stream) {
   VPS_CHECK_ARG(nlev >= 1 && nlev <= MAXLEV && out->h == out->w && out->n >= nroi, "roi_align: args");
-  const int64_t total = (int64_t)nroi * out->h * out->w * out->c;
-  if (!total) return VPS_OK;
-  VPS_DISPATCH_T(out->dtype, T, {
-    Feats<T> fs;
-    fs.n = nlev;
-    for (int i = 0; i < nlev; ++i) {
-      if (feats[i].dtype != out->dtype || feats[i].c < out->c) { vps::set_error("roi_align: level %d dtype/channels", i); return VPS_E_ARG; }
-      fs.l[i] = vps::tv<const T>(feats[i]);
-      fs.scale[i] = 1.0f / (float)strides[i];
-    }
-    roi_align_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(fs, rois, nroi, nroi_dev, vps::tv<T>(*out),
-                                                                          out->h, sample_num, total);
-  });
+  if (!((int64_t)nroi * out->h * out->w * out->c)) return VPS_OK;
+  bool vec = vps::vec_ok(*out, out->c);
+  for (int i = 0; i < nlev; ++i) {
+    VPS_CHECK_ARG(feats[i].dtype == out->dtype && feats[i].c >= out->c, "roi_align: level %d dtype/channels", i);
+    vec = vec && vps::vec_ok(feats[i], out->c);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+#define RA_LAUNCH(T, V)                                                                                     \
+  do {                                                                                                      \
+    Feats<T> fs;                                                                                            \
+    fs.n = nlev;                                                                                            \
+    for (int i = 0; i < nlev; ++i) { fs.l[i] = vps::tv<const T>(feats[i]); fs.scale[i] = 1.0f / (float)strides[i]; } \
+    for (int i = nlev; i < MAXLEV; ++i) { fs.l[i] = fs.l[nlev - 1]; fs.scale[i] = fs.scale[nlev - 1]; }       \
+    roi_align_kernel<T, V><<<vps::pix_grid(out->w, out->c / V, out->h, nroi, 128), 128, 0, st>>>(           \
+        fs, rois, nroi, nroi_dev, vps::tv<T>(*out), out->h, sample_num);                                    \
+  } while (0)
+  if (out->dtype == VPS_F32) { if (vec) RA_LAUNCH(float, 4); else RA_LAUNCH(float, 1); }
+  else { if (vec) RA_LAUNCH(__nv_bfloat16, 8); else RA_LAUNCH(__nv_bfloat16, 1); }
+#undef RA_LAUNCH
   VPS_CUDA_LAST("roi_align");
   return VPS_OK;
 }

@@ -44,72 +44,77 @@ __global__ void nhwc_to_nchw_kernel(vps::TV<const TI> src, float* __restrict__ d
   }
 }
 
-template <typename TI, typename TO>
-__global__ void axpby_kernel(vps::TV<const TI> a, vps::TV<const TI> b, int has_b, vps::TV<TO> out, float alpha,
-                             float beta, int64_t total) {
-  GRID_STRIDE(i, total) {
-    DECOMP_NHWC(i, out, n, y, x, c);
-    float v = alpha * vps::ldf<TI>(a.p + a.off(n, y, x) + c);
-    if (has_b) v += beta * vps::ldf<TI>(b.p + b.off(n, y, x) + c);
-    vps::stf<TO>(out.p + out.off(n, y, x) + c, v);
-  }
+// All kernels below use the (x*chunks, y, n) pixel grid of vps::pix_grid: no 64-bit index division, and V
+// consecutive channels (16 bytes) per thread when every tensor involved allows it (V = 1 otherwise).
+template <typename TI, typename TO, int V>
+__global__ void axpby_kernel(vps::TV<const TI> a, vps::TV<const TI> b, int has_b, vps::TV<TO> out, float alpha, float beta) {
+  VPS_PIX_COORDS(out, V, c, x, y, n);
+  float va[V], vb[V];
+  vps::ldv<TI, V>(a.p + a.off(n, y, x) + c, va);
+  if (has_b) vps::ldv<TI, V>(b.p + b.off(n, y, x) + c, vb);
+#pragma unroll
+  for (int j = 0; j < V; ++j) va[j] = alpha * va[j] + (has_b ? beta * vb[j] : 0.f);
+  vps::stv<TO, V>(out.p + out.off(n, y, x) + c, va);
 }
 
-template <typename TI, typename TO>
-__global__ void resize_bilinear_kernel(vps::TV<const TI> src, vps::TV<TO> out, float sy, float sx, float mul,
-                                       int64_t total) {
-  GRID_STRIDE(i, total) {
-    DECOMP_NHWC(i, out, n, y, x, c);
-    // area_pixel_compute_source_index(align_corners=False): max(scale*(dst+0.5)-0.5, 0)
-    float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f);
-    float fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < src.h - 1 ? 1 : 0), x1 = x0 + (x0 < src.w - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const float v00 = vps::ldf<TI>(src.p + src.off(n, y0, x0) + c);
-    const float v01 = vps::ldf<TI>(src.p + src.off(n, y0, x1) + c);
-    const float v10 = vps::ldf<TI>(src.p + src.off(n, y1, x0) + c);
-    const float v11 = vps::ldf<TI>(src.p + src.off(n, y1, x1) + c);
-    const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
-    vps::stf<TO>(out.p + out.off(n, y, x) + c, v * mul);
-  }
+template <typename TI, typename TO, int V>
+__global__ void resize_bilinear_kernel(vps::TV<const TI> src, vps::TV<TO> out, float sy, float sx, float mul) {
+  VPS_PIX_COORDS(out, V, c, x, y, n);
+  // area_pixel_compute_source_index(align_corners=False): max(scale*(dst+0.5)-0.5, 0)
+  const float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f);
+  const float fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < src.h - 1 ? 1 : 0), x1 = x0 + (x0 < src.w - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  float v00[V], v01[V], v10[V], v11[V];
+  vps::ldv<TI, V>(src.p + src.off(n, y0, x0) + c, v00);
+  vps::ldv<TI, V>(src.p + src.off(n, y0, x1) + c, v01);
+  vps::ldv<TI, V>(src.p + src.off(n, y1, x0) + c, v10);
+  vps::ldv<TI, V>(src.p + src.off(n, y1, x1) + c, v11);
+#pragma unroll
+  for (int j = 0; j < V; ++j) v00[j] = (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j])) * mul;
+  vps::stv<TO, V>(out.p + out.off(n, y, x) + c, v00);
 }
 
-template <typename TI, typename TO>
-__global__ void resize_nearest_kernel(vps::TV<const TI> src, vps::TV<TO> out, float sy, float sx, float mul,
-                                      int accumulate, int64_t total) {
-  GRID_STRIDE(i, total) {
-    DECOMP_NHWC(i, out, n, y, x, c);
-    const int ys = min((int)floorf((float)y * sy), src.h - 1);
-    const int xs = min((int)floorf((float)x * sx), src.w - 1);
-    float v = vps::ldf<TI>(src.p + src.off(n, ys, xs) + c) * mul;
-    TO* op = out.p + out.off(n, y, x) + c;
-    if (accumulate) v += vps::ldf<TO>(op);
-    vps::stf<TO>(op, v);
-  }
+template <typename TI, typename TO, int V>
+__global__ void resize_nearest_kernel(vps::TV<const TI> src, vps::TV<TO> out, float sy, float sx, float mul, int accumulate) {
+  VPS_PIX_COORDS(out, V, c, x, y, n);
+  const int ys = min((int)floorf((float)y * sy), src.h - 1);
+  const int xs = min((int)floorf((float)x * sx), src.w - 1);
+  float v[V], o[V];
+  vps::ldv<TI, V>(src.p + src.off(n, ys, xs) + c, v);
+  TO* op = out.p + out.off(n, y, x) + c;
+  if (accumulate) vps::ldv<TO, V>(op, o);
+#pragma unroll
+  for (int j = 0; j < V; ++j) v[j] = v[j] * mul + (accumulate ? o[j] : 0.f);
+  vps::stv<TO, V>(op, v);
 }
 
-template <typename TI, typename TO>
-__global__ void pool2d_kernel(vps::TV<const TI> src, vps::TV<TO> out, int k, int s, int p, int is_avg,
-                              int64_t total) {
-  GRID_STRIDE(i, total) {
-    DECOMP_NHWC(i, out, n, y, x, c);
-    const int ys = y * s - p, xs = x * s - p;
-    float acc = is_avg ? 0.f : -INFINITY;
-    for (int r = 0; r < k; ++r) {
-      const int yy = ys + r;
-      if (yy < 0 || yy >= src.h) continue;
-      for (int q = 0; q < k; ++q) {
-        const int xx = xs + q;
-        if (xx < 0 || xx >= src.w) continue;
-        const float v = vps::ldf<TI>(src.p + src.off(n, yy, xx) + c);
-        acc = is_avg ? acc + v : fmaxf(acc, v);
-      }
+template <typename TI, typename TO, int V>
+__global__ void pool2d_kernel(vps::TV<const TI> src, vps::TV<TO> out, int k, int s, int p, int is_avg) {
+  VPS_PIX_COORDS(out, V, c, x, y, n);
+  const int ys = y * s - p, xs = x * s - p;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = is_avg ? 0.f : -INFINITY;
+  for (int r = 0; r < k; ++r) {
+    const int yy = ys + r;
+    if (yy < 0 || yy >= src.h) continue;
+    for (int q = 0; q < k; ++q) {
+      const int xx = xs + q;
+      if (xx < 0 || xx >= src.w) continue;
+      float v[V];
+      vps::ldv<TI, V>(src.p + src.off(n, yy, xx) + c, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = is_avg ? acc[j] + v[j] : fmaxf(acc[j], v[j]);
     }
-    if (is_avg) acc /= (float)(k * k);  // count_include_pad=True (torch default, tcea_modules.py:28)
-    vps::stf<TO>(out.p + out.off(n, y, x) + c, acc);
   }
+  if (is_avg) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] /= (float)(k * k);   // count_include_pad=True (torch default, tcea_modules.py:28)
+  }
+  vps::stv<TO, V>(out.p + out.off(n, y, x) + c, acc);
 }
 
 // ---- GroupNorm: pass 1 = per-(n,group) sum / sumsq in double via block partials; pass 2 = apply
@@ -142,22 +147,25 @@ __global__ void gn_stats_kernel(vps::TV<const TI> x, int groups, double* __restr
     }
   }
 }
-template <typename TI, typename TO>
+template <typename TI, typename TO, int V>
 __global__ void gn_apply_kernel(vps::TV<const TI> x, vps::TV<TO> y, const double* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int groups,
-                                float eps, int relu, int64_t total) {
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                                int relu) {
+  VPS_PIX_COORDS(y, V, c, xx, yy, n);
   const int cg = x.c / groups;
   const double cnt = (double)x.h * x.w * cg;
-  GRID_STRIDE(i, total) {
-    DECOMP_NHWC(i, y, n, yy, xx, c);
-    const int g = c / cg;
+  float v[V];
+  vps::ldv<TI, V>(x.p + x.off(n, yy, xx) + c, v);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int g = (c + j) / cg;
     const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
     const double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
     const float rstd = rsqrtf((float)var + eps);
-    float v = (vps::ldf<TI>(x.p + x.off(n, yy, xx) + c) - (float)m) * rstd * gamma[c] + beta[c];
-    if (relu) v = fmaxf(v, 0.f);
-    vps::stf<TO>(y.p + y.off(n, yy, xx) + c, v);
+    float o = (v[j] - (float)m) * rstd * gamma[c + j] + beta[c + j];
+    v[j] = relu ? fmaxf(o, 0.f) : o;
   }
+  vps::stv<TO, V>(y.p + y.off(n, yy, xx) + c, v);
 }
 
 template <typename TI, typename TO>
@@ -175,6 +183,37 @@ __global__ void im2col_kernel(vps::TV<const TI> x, vps::TV<TO> cols, int kh, int
       if (iy >= 0 && iy < x.h && ix >= 0 && ix < x.w) v = vps::ldf<TI>(x.p + x.off(n, iy, ix) + ci);
     }
     vps::stf<TO>(cols.p + cols.off(n, oy, ox) + k, v);
+  }
+}
+
+// bf16 fast path: one thread = one output pixel x 8 consecutive k (one 16-byte store); (r,s,ci) is decomposed once
+// with 32-bit arithmetic and then incremented.
+__global__ void im2col_bf16x8_kernel(vps::TV<const __nv_bfloat16> x, vps::TV<__nv_bfloat16> cols, int kh, int kw, int sh,
+                                     int sw, int ph, int pw, int chunks, int64_t total) {
+  const int kk = kh * kw * x.c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    const int64_t pix = i / chunks;
+    const int ox = (int)(pix % cols.w);
+    const int64_t t = pix / cols.w;
+    const int oy = (int)(t % cols.h), n = (int)(t / cols.h);
+    int k = ch * 8;
+    int ci = k % x.c;
+    int rs = k / x.c;
+    int s = rs % kw, r = rs / kw;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = 0.f;
+      if (k < kk) {
+        const int iy = oy * sh - ph + r, ix = ox * sw - pw + s;
+        if (iy >= 0 && iy < x.h && ix >= 0 && ix < x.w) f = __bfloat162float(x.p[x.off(n, iy, ix) + ci]);
+      }
+      v[j] = __float2bfloat16_rn(f);
+      ++k;
+      if (++ci == x.c) { ci = 0; if (++s == kw) { s = 0; ++r; } }
+    }
+    *(uint4*)(cols.p + pix * cols.cs + ch * 8) = *(const uint4*)v;
   }
 }
 
@@ -217,12 +256,21 @@ extern "C" int vps_axpby(const vps_tensor* a, const vps_tensor* b, const vps_ten
                          void* stream) {
   VPS_CHECK_ARG(a->h == out->h && a->w == out->w && a->c >= out->c && a->n == out->n, "axpby: shape");
   if (b) VPS_CHECK_ARG(b->dtype == a->dtype && b->h == out->h && b->w == out->w && b->c >= out->c, "axpby: b");
-  const int64_t total = (int64_t)out->n * out->h * out->w * out->c;
-  if (!total) return VPS_OK;
-  vps_tensor bb = b ? *b : *a;
-  DISPATCH_IO(a->dtype, out->dtype, TI, TO,
-              (axpby_kernel<TI, TO><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-                  vps::tv<const TI>(*a), vps::tv<const TI>(bb), b != nullptr, vps::tv<TO>(*out), alpha, beta, total)));
+  if (!((int64_t)out->n * out->h * out->w * out->c)) return VPS_OK;
+  const vps_tensor bb = b ? *b : *a;
+  const bool vc = vps::vec_ok(*a, out->c) && vps::vec_ok(bb, out->c) && vps::vec_ok(*out, out->c);
+  const bool vec = a->dtype == out->dtype && vc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && out->dtype == VPS_F32)
+    axpby_kernel<float, float, 4><<<vps::pix_grid(out->w, out->c / 4, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const float>(*a), vps::tv<const float>(bb), b != nullptr, vps::tv<float>(*out), alpha, beta);
+  else if (vec)
+    axpby_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<vps::pix_grid(out->w, out->c / 8, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const __nv_bfloat16>(*a), vps::tv<const __nv_bfloat16>(bb), b != nullptr, vps::tv<__nv_bfloat16>(*out), alpha, beta);
+  else
+    DISPATCH_IO(a->dtype, out->dtype, TI, TO,
+                (axpby_kernel<TI, TO, 1><<<vps::pix_grid(out->w, out->c, out->h, out->n), 256, 0, st>>>(
+                    vps::tv<const TI>(*a), vps::tv<const TI>(bb), b != nullptr, vps::tv<TO>(*out), alpha, beta)));
   VPS_CUDA_LAST("axpby");
   return VPS_OK;
 }
@@ -231,24 +279,40 @@ extern "C" int vps_copy_scale(const vps_tensor* src, const vps_tensor* dst, floa
 }
 extern "C" int vps_resize_bilinear(const vps_tensor* src, const vps_tensor* out, float mul, void* stream) {
   VPS_CHECK_ARG(src->c >= out->c && src->n == out->n, "resize_bilinear: shape");
-  const int64_t total = (int64_t)out->n * out->h * out->w * out->c;
-  if (!total) return VPS_OK;
+  if (!((int64_t)out->n * out->h * out->w * out->c)) return VPS_OK;
   const float sy = (float)src->h / (float)out->h, sx = (float)src->w / (float)out->w;
-  DISPATCH_IO(src->dtype, out->dtype, TI, TO,
-              (resize_bilinear_kernel<TI, TO><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-                  vps::tv<const TI>(*src), vps::tv<TO>(*out), sy, sx, mul, total)));
+  const bool vec = src->dtype == out->dtype && vps::vec_ok(*src, out->c) && vps::vec_ok(*out, out->c);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && out->dtype == VPS_F32)
+    resize_bilinear_kernel<float, float, 4><<<vps::pix_grid(out->w, out->c / 4, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const float>(*src), vps::tv<float>(*out), sy, sx, mul);
+  else if (vec)
+    resize_bilinear_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<vps::pix_grid(out->w, out->c / 8, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const __nv_bfloat16>(*src), vps::tv<__nv_bfloat16>(*out), sy, sx, mul);
+  else
+    DISPATCH_IO(src->dtype, out->dtype, TI, TO,
+                (resize_bilinear_kernel<TI, TO, 1><<<vps::pix_grid(out->w, out->c, out->h, out->n), 256, 0, st>>>(
+                    vps::tv<const TI>(*src), vps::tv<TO>(*out), sy, sx, mul)));
   VPS_CUDA_LAST("resize_bilinear");
   return VPS_OK;
 }
 extern "C" int vps_resize_nearest(const vps_tensor* src, const vps_tensor* out, float mul, int accumulate,
                                   void* stream) {
   VPS_CHECK_ARG(src->c >= out->c && src->n == out->n, "resize_nearest: shape");
-  const int64_t total = (int64_t)out->n * out->h * out->w * out->c;
-  if (!total) return VPS_OK;
+  if (!((int64_t)out->n * out->h * out->w * out->c)) return VPS_OK;
   const float sy = (float)src->h / (float)out->h, sx = (float)src->w / (float)out->w;
-  DISPATCH_IO(src->dtype, out->dtype, TI, TO,
-              (resize_nearest_kernel<TI, TO><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-                  vps::tv<const TI>(*src), vps::tv<TO>(*out), sy, sx, mul, accumulate, total)));
+  const bool vec = src->dtype == out->dtype && vps::vec_ok(*src, out->c) && vps::vec_ok(*out, out->c);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && out->dtype == VPS_F32)
+    resize_nearest_kernel<float, float, 4><<<vps::pix_grid(out->w, out->c / 4, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const float>(*src), vps::tv<float>(*out), sy, sx, mul, accumulate);
+  else if (vec)
+    resize_nearest_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<vps::pix_grid(out->w, out->c / 8, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const __nv_bfloat16>(*src), vps::tv<__nv_bfloat16>(*out), sy, sx, mul, accumulate);
+  else
+    DISPATCH_IO(src->dtype, out->dtype, TI, TO,
+                (resize_nearest_kernel<TI, TO, 1><<<vps::pix_grid(out->w, out->c, out->h, out->n), 256, 0, st>>>(
+                    vps::tv<const TI>(*src), vps::tv<TO>(*out), sy, sx, mul, accumulate)));
   VPS_CUDA_LAST("resize_nearest");
   return VPS_OK;
 }
@@ -256,11 +320,19 @@ extern "C" int vps_pool2d(const vps_tensor* src, const vps_tensor* out, int k, i
                           void* stream) {
   VPS_CHECK_ARG(src->c >= out->c && src->n == out->n, "pool2d: shape");
   VPS_CHECK_ARG(out->h == (src->h + 2 * p - k) / s + 1 && out->w == (src->w + 2 * p - k) / s + 1, "pool2d: out size");
-  const int64_t total = (int64_t)out->n * out->h * out->w * out->c;
-  if (!total) return VPS_OK;
-  DISPATCH_IO(src->dtype, out->dtype, TI, TO,
-              (pool2d_kernel<TI, TO><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-                  vps::tv<const TI>(*src), vps::tv<TO>(*out), k, s, p, is_avg, total)));
+  if (!((int64_t)out->n * out->h * out->w * out->c)) return VPS_OK;
+  const bool vec = src->dtype == out->dtype && vps::vec_ok(*src, out->c) && vps::vec_ok(*out, out->c);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && out->dtype == VPS_F32)
+    pool2d_kernel<float, float, 4><<<vps::pix_grid(out->w, out->c / 4, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const float>(*src), vps::tv<float>(*out), k, s, p, is_avg);
+  else if (vec)
+    pool2d_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<vps::pix_grid(out->w, out->c / 8, out->h, out->n), 256, 0, st>>>(
+        vps::tv<const __nv_bfloat16>(*src), vps::tv<__nv_bfloat16>(*out), k, s, p, is_avg);
+  else
+    DISPATCH_IO(src->dtype, out->dtype, TI, TO,
+                (pool2d_kernel<TI, TO, 1><<<vps::pix_grid(out->w, out->c, out->h, out->n), 256, 0, st>>>(
+                    vps::tv<const TI>(*src), vps::tv<TO>(*out), k, s, p, is_avg)));
   VPS_CUDA_LAST("pool2d");
   return VPS_OK;
 }
@@ -287,9 +359,17 @@ extern "C" int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const flo
   dim3 grid(chunks, groups, x->n);
   VPS_DISPATCH_T(x->dtype, TI, (gn_stats_kernel<TI><<<grid, 256, 0, st>>>(vps::tv<const TI>(*x), groups, g_gn_stats)));
   VPS_CUDA_LAST("gn_stats");
-  DISPATCH_IO(x->dtype, y->dtype, TI, TO,
-              (gn_apply_kernel<TI, TO><<<grid_for(total), 256, 0, st>>>(vps::tv<const TI>(*x), vps::tv<TO>(*y), g_gn_stats,
-                                                                       gamma, beta, groups, eps, relu, total)));
+  const bool vec = x->dtype == y->dtype && vps::vec_ok(*x, x->c) && vps::vec_ok(*y, x->c);
+  if (vec && y->dtype == VPS_F32)
+    gn_apply_kernel<float, float, 4><<<vps::pix_grid(y->w, y->c / 4, y->h, y->n), 256, 0, st>>>(
+        vps::tv<const float>(*x), vps::tv<float>(*y), g_gn_stats, gamma, beta, groups, eps, relu);
+  else if (vec)
+    gn_apply_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<vps::pix_grid(y->w, y->c / 8, y->h, y->n), 256, 0, st>>>(
+        vps::tv<const __nv_bfloat16>(*x), vps::tv<__nv_bfloat16>(*y), g_gn_stats, gamma, beta, groups, eps, relu);
+  else
+    DISPATCH_IO(x->dtype, y->dtype, TI, TO,
+                (gn_apply_kernel<TI, TO, 1><<<vps::pix_grid(y->w, y->c, y->h, y->n), 256, 0, st>>>(
+                    vps::tv<const TI>(*x), vps::tv<TO>(*y), g_gn_stats, gamma, beta, groups, eps, relu)));
   VPS_CUDA_LAST("gn_apply");
   return VPS_OK;
 }
@@ -299,6 +379,18 @@ extern "C" int vps_im2col(const vps_tensor* x, const vps_tensor* cols, int kh, i
   VPS_CHECK_ARG(cols->c >= kh * kw * x->c, "im2col: cols.c %d < %d", cols->c, kh * kw * x->c);
   const int64_t total = (int64_t)cols->n * cols->h * cols->w * cols->c;
   if (!total) return VPS_OK;
+  if (x->dtype == VPS_BF16 && cols->dtype == VPS_BF16 && cols->c % 8 == 0 && cols->cs % 8 == 0 &&
+      ((uintptr_t)cols->ptr & 15) == 0) {
+    const int chunks = cols->c / 8;
+    const int64_t tot8 = total / 8;
+    int64_t blocks = (tot8 + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    im2col_bf16x8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(vps::tv<const __nv_bfloat16>(*x),
+                                                                        vps::tv<__nv_bfloat16>(*cols), kh, kw, sh, sw, ph,
+                                                                        pw, chunks, tot8);
+    VPS_CUDA_LAST("im2col_bf16x8");
+    return VPS_OK;
+  }
   DISPATCH_IO(x->dtype, cols->dtype, TI, TO,
               (im2col_kernel<TI, TO><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
                   vps::tv<const TI>(*x), vps::tv<TO>(*cols), kh, kw, sh, sw, ph, pw, total)));
