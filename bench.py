@@ -167,15 +167,12 @@ def build_product(precision, device):
 
 
 def run_gpu_arm(args):
-    import torch.distributed as dist
     from vps_b200 import ops
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from vps_b200 import parallel as P
+    rank, local, world = P.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    P.init("nccl", dev)
     H, W = args.height, args.width
     det = build_product(args.precision, dev)
     NPAIR = 4                                        # 4 distinct pairs = 201 MB of fp32 frames (> 126 MB L2)
@@ -213,22 +210,17 @@ def run_gpu_arm(args):
     for i in range(args.warmup):
         step(i, False)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    P.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.launch_count()
     ms = timed(args.steps, False, args.warmup)
     launches = ops.launch_count() - l0
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    P.barrier()
     ms_e2e = timed(args.steps, True, args.warmup + args.steps)
     sampler.stop_flag = True
-    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = [float(v) / 1e3 for v in tot.tolist()]
+    t_dev, t_e2e = [v / 1e3 for v in P.max_over_ranks([sum(ms), sum(ms_e2e)], dev)]     # max over ranks
     value = world * args.steps / t_dev
     e2e = world * args.steps / t_e2e
 
@@ -283,8 +275,9 @@ def run_gpu_arm(args):
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
+    P.barrier()
     if world > 1:
-        dist.barrier()
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 
@@ -298,9 +291,10 @@ def main():
     ap.add_argument("--height", type=int, default=H_FULL)
     ap.add_argument("--width", type=int, default=W_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs under ncu only (numbers are not bench values)")
     ap.add_argument("--profile-out", default="", help="write per-call device timings of one instrumented step (JSON lines)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.warmup = max(args.warmup, 3) if (args.impl == "b200" and not args.allow_short_warmup) else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -45,6 +45,8 @@ const char* vps_last_error(void);
 int vps_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 int64_t vps_launch_count(void);
+/* a CUDA-graph replay re-launches kernels without going through the C entry points: the caller reports them */
+void vps_add_launch_count(int64_t n);
 
 /* ---- dense contractions -------------------------------------------------------------------- */
 /*
@@ -61,7 +63,7 @@ int64_t vps_launch_count(void);
  *
  * vps_conv2d_tc   : bf16 operands, fp32 accumulation on tcgen05 tensor cores (TMA im2col tiles,
  *                   accumulators in TMEM).  w = bf16 [cout_pad][kh*kw*cin_pad] (ci fastest,
- *                   cin_pad = cin rounded up to 64, cout_pad to 16), produced by vps_pack_weights_tc.
+ *                   cin_pad = cin rounded up to cin_gran (64 or 16), cout_pad to 16), from vps_pack_weights_tc.
  *                   x must be VPS_BF16 with cs % 8 == 0 and 16-byte aligned ptr.
  * vps_conv2d_simt : fp32 (or bf16 storage) direct convolution on CUDA cores with fp32 FMA --
  *                   the parity-mode path and the path for tiny channel counts.
@@ -80,18 +82,22 @@ typedef struct vps_conv_args {
   float slope;
   int32_t res_after_act;
   float out_scale;            /* y = out_scale * act(...) ; 1.0 normally (FlowNet2 div_flow folds here) */
+  int32_t cin_gran;           /* tc only: 64 (default, 0) or 16 = channel granularity of the packed weights / K step */
 } vps_conv_args;
 
 int vps_conv2d_tc(const vps_conv_args* a, void* stream);
+/* up to 4 problems sharing x / y / geometry / bias / activation and differing in w, (ph,pw) and (oy_off,ox_off):
+ * the stride phases of a ConvTranspose2d (submodules.py:33-37, fcn_mask_head.py:66-71) in one persistent launch. */
+int vps_conv2d_tc_multi(const vps_conv_args* a, int nprob, void* stream);
 int vps_conv2d_simt(const vps_conv_args* a, void* stream);
 /* OIHW fp32 (torch layout, on device) -> packed layouts.  scale[cout] (may be NULL) is folded in
  * (frozen BatchNorm: resnet.py:519-526).  transposed != 0: src is IOHW (ConvTranspose2d). */
 int vps_pack_weights_tc(const float* w_oihw, const float* scale, void* dst_bf16, int cout, int cin,
-                        int kh, int kw, int transposed, void* stream);
+                        int kh, int kw, int transposed, int cin_gran, void* stream);
 int vps_pack_weights_simt(const float* w_oihw, const float* scale, float* dst, int cout, int cin,
                           int kh, int kw, int transposed, void* stream);
 /* bytes of the packed tc weight buffer */
-int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw);
+int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw, int cin_gran);
 
 /* explicit im2col for small-cin layers feeding vps_conv2d_tc as a 1x1 conv: cols is NHWC
  * [n, oh, ow, kpad] with k = (r*kw+s)*cin + ci, zero padded to cols.c. */
@@ -104,6 +110,12 @@ int vps_im2col(const vps_tensor* x, const vps_tensor* cols, int kh, int kw, int 
  * Optional fused LeakyReLU (FlowNetC.py:33,87).  f1,f2,out NHWC. */
 int vps_correlation(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
                     int max_disp, int stride1, int stride2, int act, float slope, void* stream);
+/* the two implementations behind vps_correlation: banded GEMM on tcgen05 (bf16 features, C % 64 == 0, C <= 256,
+ * the (pad 20, d 20, s2 2) and (pad 4, d 4, s2 1) call sites) and the CUDA-core kernel (any dtype; parity mode). */
+int vps_correlation_tc(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
+                       int max_disp, int stride1, int stride2, int act, float slope, void* stream);
+int vps_correlation_simt(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
+                         int max_disp, int stride1, int stride2, int act, float slope, void* stream);
 /* resample2d_cuda.forward (resample2d_cuda.cc:6-31, resample2d_kernel.cu:16-71): bilinear warp by
  * pixel-unit flow (channel 0 = x), border-clamped taps, kernel_size 1. */
 int vps_resample2d(const vps_tensor* src, const vps_tensor* flow, const vps_tensor* out, void* stream);
@@ -116,6 +128,12 @@ int vps_channelnorm(const vps_tensor* a, const vps_tensor* b, const vps_tensor* 
  * (img 0..2, ref 3..5).  std3/mean3 are HOST arrays of 3 floats; sums_ws = 3 device doubles. */
 int vps_flownet_input(const float* img_nchw, const float* ref_nchw, int H, int W, const float* std3,
                       const float* mean3, float rgb_max, double* sums_ws, const vps_tensor* x, void* stream);
+
+/* nn.ConvTranspose2d(2, 2, 4, 2, 1): the `upsampled_flow*_to_*` layers of every FlowNet (FlowNetS.py:45-48,
+ * FlowNetC.py:48-51, FlowNetSD.py:45-48, FlowNetFusion.py:34-35).  w_iohw_host = 64 HOST floats [ci][co][ky][kx],
+ * bias_host = 2 HOST floats or NULL (they travel as kernel arguments); x [n,h,w,2] -> y [n,2h,2w,2] (a concat slice). */
+int vps_flow_deconv(const vps_tensor* x, const float* w_iohw_host, const float* bias_host, const vps_tensor* y,
+                    void* stream);
 
 /* ---- layout / pointwise / resampling --------------------------------------------------------- */
 int vps_nchw_to_nhwc(const float* src, const vps_tensor* dst, void* stream);   /* src [n,c,h,w] f32 */
@@ -131,6 +149,9 @@ int vps_resize_bilinear(const vps_tensor* src, const vps_tensor* out, float mul,
 /* F.interpolate nearest: src index = floor(dst * in/out) (fpn.py:112-113, flownet2.py:72-73);
  * accumulate != 0: out += (FPN top-down add). */
 int vps_resize_nearest(const vps_tensor* src, const vps_tensor* out, float mul, int accumulate, void* stream);
+/* space-to-depth, block 2: y[n,Y,X,(dy*2+dx)*C+c] = x[n,2Y+dy,2X+dx,c].  Lets the 7x7 stride-2 stem convolutions
+ * (resnet.py:436-451, FlowNetC.py:20 / FlowNetS.py:20 conv1) run as 4x4 stride-1 implicit GEMMs on the tensor cores. */
+int vps_space_to_depth2(const vps_tensor* x, const vps_tensor* y, void* stream);
 /* max / avg pool (resnet.py:451, tcea_modules.py:27-28; avg = count_include_pad) */
 int vps_pool2d(const vps_tensor* src, const vps_tensor* out, int k, int s, int p, int is_avg, void* stream);
 /* GroupNorm(groups, eps) + optional ReLU (upsnetFPN.py:42-51) */

@@ -87,7 +87,7 @@ def test_state_dict_layout_matches_oracle_and_reference_names():
 def test_cabi_library_exports_every_declared_symbol():
     from vps_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "vps_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:const char\*|int64_t|int)\s+(vps_[a-z0-9_]+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^\s*(?:const char\*|int64_t|int|void)\s+(vps_[a-z0-9_]+)\s*\(", hdr, re.M))
     assert len(declared) >= 40
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     lib = ctypes.CDLL(_lib.LIB_PATH)

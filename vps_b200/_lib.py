@@ -26,7 +26,7 @@ class VpsConvArgs(C.Structure):
                 ("oy_mul", C.c_int32), ("oy_off", C.c_int32), ("ox_mul", C.c_int32), ("ox_off", C.c_int32),
                 ("cin", C.c_int32), ("cout", C.c_int32),
                 ("act", C.c_int32), ("slope", C.c_float), ("res_after_act", C.c_int32),
-                ("out_scale", C.c_float)]
+                ("out_scale", C.c_float), ("cin_gran", C.c_int32)]
 
 
 class VpsError(RuntimeError):
@@ -48,6 +48,8 @@ def lib():
         _lib.vps_last_error.restype = C.c_char_p
         _lib.vps_launch_count.restype = C.c_int64
         _lib.vps_packed_tc_bytes.restype = C.c_int64
+        _lib.vps_add_launch_count.restype = None
+        _lib.vps_add_launch_count.argtypes = [C.c_int64]
     return _lib
 
 
@@ -58,12 +60,12 @@ def check(status, what=""):
 
 # every symbol include/vps_b200.h declares (tests assert the .so exports all of them)
 EXPORTS = [
-    "vps_last_error", "vps_version", "vps_launch_count",
-    "vps_conv2d_tc", "vps_conv2d_simt", "vps_pack_weights_tc", "vps_pack_weights_simt",
+    "vps_last_error", "vps_version", "vps_launch_count", "vps_add_launch_count",
+    "vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_conv2d_simt", "vps_pack_weights_tc", "vps_pack_weights_simt",
     "vps_packed_tc_bytes", "vps_im2col",
-    "vps_correlation", "vps_resample2d", "vps_channelnorm", "vps_flownet_input",
+    "vps_correlation", "vps_correlation_tc", "vps_correlation_simt", "vps_resample2d", "vps_channelnorm", "vps_flownet_input", "vps_flow_deconv",
     "vps_nchw_to_nhwc", "vps_nhwc_to_nchw", "vps_copy_scale", "vps_axpby",
-    "vps_resize_bilinear", "vps_resize_nearest", "vps_pool2d", "vps_groupnorm",
+    "vps_space_to_depth2", "vps_resize_bilinear", "vps_resize_nearest", "vps_pool2d", "vps_groupnorm",
     "vps_bfp_gather", "vps_bfp_scatter", "vps_flow_warp", "vps_tcea_temporal", "vps_tcea_combine",
     "vps_deform_im2col",
     "vps_roi_align", "vps_sort_desc", "vps_rpn_decode", "vps_nms", "vps_sigmoid_flat", "vps_gather_rows",

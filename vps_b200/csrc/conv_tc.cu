@@ -25,14 +25,17 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int NUM_EPI_WARPS = 8;                      // 2 per TMEM lane quarter, alternating 32-column chunks
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 
+constexpr int MAX_PROB = 4;   // stride-phase sub-convolutions of one transposed conv share a launch
+
 struct ConvTcParams {
+  int bk;                     // K elements per pipeline stage: 64 (SWIZZLE_128B rows) or 16 (SWIZZLE_32B rows)
+  int nprob, tiles_per_prob;  // problems differ only in weights, padding and output pixel offset
+  int ph_[MAX_PROB], pw_[MAX_PROB], oy_off_[MAX_PROB], ox_off_[MAX_PROB];
   int n_img, oh, ow;
   int th, tw, tiles_y, tiles_x;
   int n_tiles_n, block_n;
@@ -122,13 +125,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+// K-major operand tile whose rows are bk*2 bytes: bk=64 -> 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart;
+// bk=16 -> 32-byte rows, SWIZZLE_32B, 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int bk) {
   uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
+  d |= (uint64_t)((bk == 64 ? 1024 : 256) >> 4) << 32;         // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                                      // descriptor version (sm_100)
+  d |= (uint64_t)(bk == 64 ? 2 : 6) << 61;                     // layout type SWIZZLE_128B / SWIZZLE_32B
   return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
@@ -253,14 +257,16 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int n_idx = tile % p.n_tiles_n;
-    const int m_idx = tile / p.n_tiles_n;
+    const int prob = tile / p.tiles_per_prob;
+    const int t_in = tile - prob * p.tiles_per_prob;
+    const int n_idx = t_in % p.n_tiles_n;
+    const int m_idx = t_in / p.n_tiles_n;
     const int img = m_idx / tiles_per_img;
     const int rem = m_idx - img * tiles_per_img;
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
     const int oy = ty * p.th + ty_in, ox = tx * p.tw + tx_in;
     const bool valid = (oy < p.oh) && (ox < p.ow);
-    const int64_t pix = ((int64_t)img * p.y_h + (oy * p.oy_mul + p.oy_off)) * p.y_w + (ox * p.ox_mul + p.ox_off);
+    const int64_t pix = ((int64_t)img * p.y_h + (oy * p.oy_mul + p.oy_off_[prob])) * p.y_w + (ox * p.ox_mul + p.ox_off_[prob]);
     const int nbase = n_idx * p.block_n;
 
     mbar_wait(tfull0 + 8u * acc, acc_phase);
@@ -291,12 +297,15 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
 
 // ---------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const ConvTcParams p) {
+conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                     const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                     const __grid_constant__ CUtensorMap tmB3, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned operand ring (SWIZZLE_128B requirement)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.block_n * 128u;
+  const uint32_t row_bytes = (uint32_t)p.bk * 2u;
+  const uint32_t a_stage_bytes = BLOCK_M * row_bytes;
+  const uint32_t stage_bytes = a_stage_bytes + (uint32_t)p.block_n * row_bytes;
   const uint32_t bar_base = smem_base + (uint32_t)p.num_stages * stage_bytes;
   // barrier slots (8 B each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -319,7 +328,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -342,23 +351,25 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % p.n_tiles_n;
-        const int m_idx = tile / p.n_tiles_n;
+        const int prob = tile / p.tiles_per_prob;
+        const int t_in = tile - prob * p.tiles_per_prob;
+        const int n_idx = t_in % p.n_tiles_n;
+        const int m_idx = t_in / p.n_tiles_n;
         const int img = m_idx / tiles_per_img;
         const int rem = m_idx - img * tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int x_base = tx * p.tw * p.sw - p.pw;
-        const int y_base = ty * p.th * p.sh - p.ph;
+        const int x_base = tx * p.tw * p.sw - p.pw_[prob];
+        const int y_base = ty * p.th * p.sh - p.ph_[prob];
+        const CUtensorMap* tmB = prob == 0 ? &tmB0 : (prob == 1 ? &tmB1 : (prob == 2 ? &tmB2 : &tmB3));
         for (int r = 0; r < p.kh; ++r) {
           for (int s = 0; s < p.kw; ++s) {
             for (int cc = 0; cc < p.cin_chunks; ++cc) {
               mbar_wait(empty_bar(stage), phase ^ 1);
               const uint32_t a_dst = smem_base + stage * stage_bytes;
-              const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+              const uint32_t b_dst = a_dst + a_stage_bytes;
               mbar_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_4d(a_dst, &tmA, full_bar(stage), cc * BLOCK_K, x_base + s, y_base + r, img);
-              tma_load_2d(b_dst, &tmB, full_bar(stage), ((r * p.kw + s) * p.cin_chunks + cc) * BLOCK_K,
-                          n_idx * p.block_n);
+              tma_load_4d(a_dst, &tmA, full_bar(stage), cc * p.bk, x_base + s, y_base + r, img);
+              tma_load_2d(b_dst, tmB, full_bar(stage), ((r * p.kw + s) * p.cin_chunks + cc) * p.bk, n_idx * p.block_n);
               if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -383,11 +394,11 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+          const uint64_t adesc = make_smem_desc(a_addr, p.bk);
+          const uint64_t bdesc = make_smem_desc(a_addr + a_stage_bytes, p.bk);
+          const int nk = p.bk >> 4;
+          for (int k = 0; k < nk; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                       (uint32_t)((kc | k) != 0));
           }
@@ -461,14 +472,16 @@ int g_num_sms = 0;
 
 }  // namespace
 
-extern "C" int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw) {
-  const int64_t cout_pad = (cout + 15) / 16 * 16, cin_pad = (cin + 63) / 64 * 64;
+static inline int cin_pad_for(int cin, int gran) { return (cin + gran - 1) / gran * gran; }
+
+extern "C" int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw, int cin_gran) {
+  const int64_t cout_pad = (cout + 15) / 16 * 16, cin_pad = cin_pad_for(cin, cin_gran == 16 ? 16 : 64);
   return cout_pad * kh * kw * cin_pad * 2;
 }
 
-extern "C" int vps_pack_weights_tc(const float* w, const float* scale, void* dst, int cout, int cin, int kh,
-                                   int kw, int transposed, void* stream) {
-  const int cout_pad = (cout + 15) / 16 * 16, cin_pad = (cin + 63) / 64 * 64;
+extern "C" int vps_pack_weights_tc(const float* w, const float* scale, void* dst, int cout, int cin, int kh, int kw,
+                                   int transposed, int cin_gran, void* stream) {
+  const int cout_pad = (cout + 15) / 16 * 16, cin_pad = cin_pad_for(cin, cin_gran == 16 ? 16 : 64);
   const int64_t total = (int64_t)cout_pad * kh * kw * cin_pad;
   const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   pack_weights_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, scale, (__nv_bfloat16*)dst, cout, cin, kh,
@@ -477,13 +490,24 @@ extern "C" int vps_pack_weights_tc(const float* w, const float* scale, void* dst
   return VPS_OK;
 }
 
-extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) {
+// nprob problems (<= 4) that share x / y / geometry / epilogue and differ in weights, padding and output pixel
+// offset: the four stride phases of a transposed convolution run as ONE persistent launch.
+extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* stream) {
+  VPS_CHECK_ARG(nprob >= 1 && nprob <= MAX_PROB, "conv2d_tc: nprob %d", nprob);
+  const vps_conv_args* a = &args[0];
   VPS_CHECK_ARG(a->x.dtype == VPS_BF16, "conv2d_tc: x must be bf16");
   VPS_CHECK_ARG(a->x.cs % 8 == 0 && ((uintptr_t)a->x.ptr & 15) == 0, "conv2d_tc: x not 16B aligned (cs=%d)",
                 a->x.cs);
   VPS_CHECK_ARG(a->sh >= 1 && a->sh <= 2 && a->sw >= 1 && a->sw <= 2, "conv2d_tc: stride must be 1 or 2");
   VPS_CHECK_ARG(a->cin == a->x.c, "conv2d_tc: cin %d != x.c %d", a->cin, a->x.c);
-  VPS_CHECK_ARG(((uintptr_t)a->w & 15) == 0, "conv2d_tc: weights not aligned");
+  for (int i = 0; i < nprob; ++i) {
+    VPS_CHECK_ARG(((uintptr_t)args[i].w & 15) == 0, "conv2d_tc: weights not aligned");
+    VPS_CHECK_ARG(args[i].x.ptr == a->x.ptr && args[i].y.ptr == a->y.ptr && args[i].kh == a->kh && args[i].kw == a->kw &&
+                      args[i].oh == a->oh && args[i].ow == a->ow && args[i].cout == a->cout && args[i].bias == a->bias &&
+                      args[i].act == a->act && args[i].oy_mul == a->oy_mul && args[i].ox_mul == a->ox_mul &&
+                      args[i].cin_gran == a->cin_gran,
+                  "conv2d_tc_multi: problems must share geometry");
+  }
   auto encode = get_encode();
   if (!encode) { vps::set_error("cuTensorMapEncodeTiled unavailable"); return VPS_E_CUDA; }
   if (!g_num_sms) {
@@ -494,7 +518,9 @@ extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) {
   }
 
   ConvTcParams p;
-  const int cin_pad = (a->cin + 63) / 64 * 64;
+  const int bk = a->cin_gran == 16 ? 16 : 64;
+  p.bk = bk;
+  const int cin_pad = cin_pad_for(a->cin, bk);
   const int cout_pad = (a->cout + 15) / 16 * 16;
   p.n_img = a->x.n; p.oh = a->oh; p.ow = a->ow;
   // pixel patch: minimise padded area; th*tw == 128, box extent tw*sw <= 256
@@ -508,79 +534,93 @@ extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) {
   }
   p.tw = best_tw; p.th = 128 / best_tw;
   p.tiles_x = vps::cdiv(a->ow, p.tw); p.tiles_y = vps::cdiv(a->oh, p.th);
-  // N tile: whole cout_pad if <= 256, else the largest multiple of 16 <= 256 dividing it
-  int block_n = cout_pad;
-  if (block_n > 256) {
-    block_n = 256;
-    while (cout_pad % block_n) block_n -= 16;
-  }
-  // small problems: shrink the N tile until the persistent grid is filled (more, smaller tiles; A re-reads hit L2)
+  // N tile: pick the divisor of cout_pad (multiple of 16, <= 256) that minimises a simple time model
+  //   waves(bn) * k_steps * max(fixed per-step latency, MMA time 2*bn clk, stage bytes / per-SM L2 bandwidth)
+  // -- large tiles when there is enough parallelism, smaller N tiles to fill the persistent grid otherwise.
+  int block_n = 16;
   {
-    const int64_t m_tiles = (int64_t)a->x.n * p.tiles_y * p.tiles_x;
-    while (m_tiles * (cout_pad / block_n) < g_num_sms && block_n >= 64 && (block_n / 2) % 16 == 0 &&
-           cout_pad % (block_n / 2) == 0)
-      block_n /= 2;
+    const int64_t m_tiles = (int64_t)a->x.n * p.tiles_y * p.tiles_x * nprob;
+    double best = -1.0;
+    for (int bn = 16; bn <= 256 && bn <= cout_pad; bn += 16) {
+      if (cout_pad % bn) continue;
+      const int64_t tiles = m_tiles * (cout_pad / bn);
+      const double waves = (double)((tiles + g_num_sms - 1) / g_num_sms);
+      const double step = fmax(fmax(350.0, 2.0 * bn), (double)((BLOCK_M + bn) * bk * 2) / 80.0);
+      const double epi = 40.0 * bn;     // epilogue clocks per tile (not hidden when a CTA runs a single tile)
+      const double t = waves * ((double)(a->kh * a->kw * (cin_pad / bk)) * step + epi);
+      if (best < 0 || t < best * 0.999) { best = t; block_n = bn; }
+    }
   }
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
-  p.kh = a->kh; p.kw = a->kw; p.sh = a->sh; p.sw = a->sw; p.ph = a->ph; p.pw = a->pw;
-  p.cin_chunks = cin_pad / 64;
-  const int stage_bytes = A_STAGE_BYTES + block_n * 128;
+  p.kh = a->kh; p.kw = a->kw; p.sh = a->sh; p.sw = a->sw;
+  p.cin_chunks = cin_pad / bk;
+  const int stage_bytes = (BLOCK_M + block_n) * bk * 2;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.num_stages = stages;
-  p.total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  p.nprob = nprob;
+  p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  p.total_tiles = p.tiles_per_prob * nprob;
   p.y = a->y.ptr; p.y_h = a->y.h; p.y_w = a->y.w; p.y_cs = a->y.cs; p.y_dtype = a->y.dtype;
   const int esz = a->y.dtype == VPS_BF16 ? 2 : 4;
   p.y_vec = (((uintptr_t)a->y.ptr & 15) == 0) && ((a->y.cs * esz) % 16 == 0);
-  p.oy_mul = a->oy_mul; p.oy_off = a->oy_off; p.ox_mul = a->ox_mul; p.ox_off = a->ox_off;
+  p.oy_mul = a->oy_mul; p.ox_mul = a->ox_mul;
+  for (int i = 0; i < MAX_PROB; ++i) {
+    const vps_conv_args* q = &args[i < nprob ? i : 0];
+    p.ph_[i] = q->ph; p.pw_[i] = q->pw; p.oy_off_[i] = q->oy_off; p.ox_off_[i] = q->ox_off;
+    VPS_CHECK_ARG((a->oh - 1) * a->oy_mul + q->oy_off < a->y.h && (a->ow - 1) * a->ox_mul + q->ox_off < a->y.w,
+                  "conv2d_tc: output mapping out of range");
+  }
   p.res = a->res.ptr; p.res_cs = a->res.cs; p.res_dtype = a->res.dtype; p.res_after_act = a->res_after_act;
   p.res_vec = a->res.ptr && (((uintptr_t)a->res.ptr & 15) == 0) && (a->res.cs % 8 == 0);
   VPS_CHECK_ARG(!a->bias || ((uintptr_t)a->bias & 15) == 0, "conv2d_tc: bias must be 16-byte aligned");
   p.bias = a->bias; p.cout = a->cout; p.act = a->act; p.slope = a->slope; p.out_scale = a->out_scale;
-  VPS_CHECK_ARG((a->oh - 1) * a->oy_mul + a->oy_off < a->y.h && (a->ow - 1) * a->ox_mul + a->ox_off < a->y.w,
-                "conv2d_tc: output mapping out of range");
   if (a->res.ptr) VPS_CHECK_ARG(a->res.h == a->y.h && a->res.w == a->y.w, "conv2d_tc: residual geometry");
   if (p.total_tiles == 0) return VPS_OK;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB[MAX_PROB];
+  const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->x.c, (cuuint64_t)a->x.w, (cuuint64_t)a->x.h, (cuuint64_t)a->x.n};
     cuuint64_t strides[3] = {(cuuint64_t)a->x.cs * 2, (cuuint64_t)a->x.w * a->x.cs * 2,
                              (cuuint64_t)a->x.h * a->x.w * a->x.cs * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(p.tw * a->sw), (cuuint32_t)(p.th * a->sh), 1};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.tw * a->sw), (cuuint32_t)(p.th * a->sh), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)a->sw, (cuuint32_t)a->sh, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      vps::set_error("conv2d_tc: encode A failed (%d) dims %d,%d,%d,%d cs %d box %d,%d", (int)r, a->x.c,
-                     a->x.w, a->x.h, a->x.n, a->x.cs, p.tw * a->sw, p.th * a->sh);
+      vps::set_error("conv2d_tc: encode A failed (%d) dims %d,%d,%d,%d cs %d box %d,%d,%d", (int)r, a->x.c,
+                     a->x.w, a->x.h, a->x.n, a->x.cs, bk, p.tw * a->sw, p.th * a->sh);
       return VPS_E_CUDA;
     }
   }
-  {
+  for (int i = 0; i < MAX_PROB; ++i) {
+    const vps_conv_args* q = &args[i < nprob ? i : 0];
     const cuuint64_t K = (cuuint64_t)a->kh * a->kw * cin_pad;
     cuuint64_t dims[2] = {K, (cuuint64_t)cout_pad};
     cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)q->w, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
   const int smem = stages * stage_bytes + 1024 + 8 * (2 * MAX_STAGES + 8);
-  static int smem_set = 0;
-  if (smem_set < smem) {
+  static bool smem_set = false;
+  if (!smem_set) {
     if (cudaFuncSetAttribute(conv_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
       vps::set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(cudaGetLastError()));
       return VPS_E_CUDA;
     }
-    smem_set = 227 * 1024;
+    smem_set = true;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_igemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  conv_igemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], p);
   VPS_CUDA_LAST("conv_igemm_tc_kernel");
   return VPS_OK;
 }
+
+extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) { return vps_conv2d_tc_multi(a, 1, stream); }

@@ -153,27 +153,54 @@ __global__ void nms_mask_kernel(int n_cap, const int* __restrict__ n_dev, float 
 }
 
 // The host greedy loop of the reference (nms_kernel.cu:104-123) as a single-block device pass: no D2H.
-__global__ void nms_reduce_kernel(int n_cap, const int* __restrict__ n_dev, const unsigned long long* __restrict__ mask,
-                                  int col_blocks, int32_t* __restrict__ keep, int* __restrict__ nkeep) {
-  extern __shared__ unsigned long long remv[];
+// Thread j keeps suppression word j in a register.  Per chunk of 64 boxes: (1) the 64 diagonal mask words are
+// fetched in parallel, (2) one thread resolves the intra-chunk greedy order with register bit-ops, (3) every thread
+// ORs the rows of the boxes kept in this chunk into its word (coalesced, independent loads).
+__global__ void __launch_bounds__(128) nms_reduce_kernel(int n_cap, const int* __restrict__ n_dev,
+                                                         const unsigned long long* __restrict__ mask, int col_blocks,
+                                                         int32_t* __restrict__ keep, int* __restrict__ nkeep) {
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_cur, s_kept;
+  __shared__ int s_num;
   const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int cb = (n + 63) / 64;
-  for (int j = threadIdx.x; j < cb; j += blockDim.x) remv[j] = 0ULL;
-  __shared__ int s_num;
-  if (threadIdx.x == 0) s_num = 0;
+  const int j = threadIdx.x;
+  unsigned long long remv = 0ULL;      // thread j < cb owns word j
+  if (j == 0) s_num = 0;
   __syncthreads();
-  for (int i = 0; i < n; ++i) {
-    const int nb = i >> 6, ib = i & 63;
-    const bool kept = !(remv[nb] & (1ULL << ib));   // all threads read the same word
+  for (int c = 0; c < cb; ++c) {
+    if (j == c) s_cur = remv;
+    if (j < 64) {
+      const int i = c * 64 + j;
+      diag[j] = (i < n) ? mask[(int64_t)i * col_blocks + c] : 0ULL;
+    }
     __syncthreads();
-    if (kept) {
-      if (threadIdx.x == 0) keep[s_num++] = i;
-      const unsigned long long* p = mask + (int64_t)i * col_blocks;
-      for (int j = nb + threadIdx.x; j < cb; j += blockDim.x) remv[j] |= p[j];
+    if (j == 0) {
+      unsigned long long cur = s_cur, kept = 0ULL;
+      const int lim = min(64, n - c * 64);
+      int num = s_num;
+      for (int i = 0; i < lim; ++i) {
+        if (!((cur >> i) & 1ULL)) {
+          kept |= 1ULL << i;
+          cur |= diag[i];
+          keep[num++] = c * 64 + i;
+        }
+      }
+      s_kept = kept;
+      s_num = num;
+    }
+    __syncthreads();
+    if (j > c && j < cb) {
+      unsigned long long kept = s_kept;
+      while (kept) {
+        const int i = __ffsll((long long)kept) - 1;
+        kept &= kept - 1;
+        remv |= mask[(int64_t)(c * 64 + i) * col_blocks + j];
+      }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *nkeep = s_num;
+  if (j == 0) *nkeep = s_num;
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n_cap,
@@ -503,11 +530,11 @@ extern "C" int vps_nms(const float* dets, int n, const int* n_dev, float thr, in
   if (n <= 0) { cudaMemsetAsync(nkeep, 0, sizeof(int), st); return VPS_OK; }
   const int col_blocks = (n + 63) / 64;
   VPS_CHECK_ARG(ws_bytes >= (int64_t)n * col_blocks * 8, "nms: workspace too small");
-  VPS_CHECK_ARG(col_blocks * 8 <= 48 * 1024, "nms: n too large");
+  VPS_CHECK_ARG(col_blocks <= 128, "nms: n %d too large (max 8192)", n);
   dim3 grid(col_blocks, col_blocks);
   nms_mask_kernel<<<grid, 64, 0, st>>>(n, n_dev, thr, dets, (unsigned long long*)ws, col_blocks);
   VPS_CUDA_LAST("nms_mask");
-  nms_reduce_kernel<<<1, 256, col_blocks * 8, st>>>(n, n_dev, (const unsigned long long*)ws, col_blocks, keep_idx, nkeep);
+  nms_reduce_kernel<<<1, 128, 0, st>>>(n, n_dev, (const unsigned long long*)ws, col_blocks, keep_idx, nkeep);
   VPS_CUDA_LAST("nms_reduce");
   return VPS_OK;
 }

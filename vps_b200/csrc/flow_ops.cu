@@ -161,8 +161,25 @@ inline int grid_for(int64_t total, int threads) {
 
 }  // namespace
 
+extern "C" int vps_correlation_tc(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad, int max_disp,
+                                  int stride1, int stride2, int act, float slope, void* stream);
+
+extern "C" int vps_correlation_simt(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
+                                    int max_disp, int stride1, int stride2, int act, float slope, void* stream);
+
+// dispatcher: bf16 features with C % 64 == 0 (<= 256) and 16-byte aligned views go to the tensor-core kernel
 extern "C" int vps_correlation(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
                                int max_disp, int stride1, int stride2, int act, float slope, void* stream) {
+  const bool tc = f1->dtype == VPS_BF16 && f2->dtype == VPS_BF16 && f1->c % 64 == 0 && f1->c <= 256 && f1->cs % 8 == 0 &&
+                  f2->cs % 8 == 0 && ((uintptr_t)f1->ptr & 15) == 0 && ((uintptr_t)f2->ptr & 15) == 0 && stride1 == 1 &&
+                  pad == max_disp && ((max_disp == 20 && stride2 == 2) || (max_disp == 4 && stride2 == 1)) &&
+                  (act == VPS_ACT_NONE || act == VPS_ACT_LRELU);
+  if (tc) return vps_correlation_tc(f1, f2, out, pad, max_disp, stride1, stride2, act, slope, stream);
+  return vps_correlation_simt(f1, f2, out, pad, max_disp, stride1, stride2, act, slope, stream);
+}
+
+extern "C" int vps_correlation_simt(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
+                                    int max_disp, int stride1, int stride2, int act, float slope, void* stream) {
   VPS_CHECK_ARG(stride1 == 1 && pad == max_disp, "correlation: only stride1=1, pad==max_displacement");
   VPS_CHECK_ARG(f1->dtype == f2->dtype && f1->dtype == out->dtype, "correlation: dtype mismatch");
   VPS_CHECK_ARG(f1->h == f2->h && f1->w == f2->w && f1->c == f2->c && out->h == f1->h && out->w == f1->w,
@@ -275,5 +292,57 @@ extern "C" int vps_flownet_input(const float* img_nchw, const float* ref_nchw, i
   VPS_DISPATCH_T(x->dtype, T, (flownet_input_kernel<T><<<grid_for(hw * 6, 256), 256, 0, st>>>(img_nchw, ref_nchw, hw, s, m,
                                                                                             sums_ws, rgb_max, vps::tv<T>(*x))));
   VPS_CUDA_LAST("flownet_input");
+  return VPS_OK;
+}
+
+// ------------------------------------------------------------------ 2->2 channel flow up-sampler
+// nn.ConvTranspose2d(2, 2, 4, 2, 1) -- `upsampled_flow*_to_*` of every FlowNet (FlowNetS.py:45-48 etc.).
+// One thread per output pixel, both output channels; weights [ci][co][ky][kx] (torch IOHW) in registers.
+namespace {
+struct DeconvW { float w[2][2][4][4]; float b[2]; };
+
+template <typename TI, typename TO>
+__global__ void flow_deconv_kernel(vps::TV<const TI> x, vps::TV<TO> y, DeconvW W) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
+  if (ox >= y.w) return;
+  const int qy = oy >> 1, py = oy & 1, qx = ox >> 1, px = ox & 1;
+  // out[2q+p]: p=0 -> (iy=q-1, ky=3), (iy=q, ky=1);  p=1 -> (iy=q, ky=2), (iy=q+1, ky=0)
+  const int iy0 = py ? qy : qy - 1, ky0 = py ? 2 : 3, ky1 = py ? 0 : 1;
+  const int ix0 = px ? qx : qx - 1, kx0 = px ? 2 : 3, kx1 = px ? 0 : 1;
+  float acc0 = W.b[0], acc1 = W.b[1];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int iy = iy0 + a, ky = a ? ky1 : ky0;
+    if (iy < 0 || iy >= x.h) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ix = ix0 + b, kx = b ? kx1 : kx0;
+      if (ix < 0 || ix >= x.w) continue;
+      const TI* xp = x.p + x.off(n, iy, ix);
+      const float v0 = vps::ldf<TI>(xp), v1 = vps::ldf<TI>(xp + 1);
+      acc0 += v0 * W.w[0][0][ky][kx] + v1 * W.w[1][0][ky][kx];
+      acc1 += v0 * W.w[0][1][ky][kx] + v1 * W.w[1][1][ky][kx];
+    }
+  }
+  TO* yp = y.p + y.off(n, oy, ox);
+  vps::stf<TO>(yp, acc0);
+  vps::stf<TO>(yp + 1, acc1);
+}
+}  // namespace
+
+extern "C" int vps_flow_deconv(const vps_tensor* x, const float* w_iohw_host, const float* bias_host, const vps_tensor* y,
+                               void* stream) {
+  VPS_CHECK_ARG(x->c == 2 && y->c == 2 && y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n, "flow_deconv: shapes");
+  DeconvW W;
+  for (int i = 0; i < 64; ++i) (&W.w[0][0][0][0])[i] = w_iohw_host[i];
+  W.b[0] = bias_host ? bias_host[0] : 0.f;
+  W.b[1] = bias_host ? bias_host[1] : 0.f;
+  dim3 grid(vps::cdiv(y->w, 128), y->h, y->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x->dtype == VPS_F32 && y->dtype == VPS_F32) flow_deconv_kernel<float, float><<<grid, 128, 0, st>>>(vps::tv<const float>(*x), vps::tv<float>(*y), W);
+  else if (x->dtype == VPS_F32) flow_deconv_kernel<float, __nv_bfloat16><<<grid, 128, 0, st>>>(vps::tv<const float>(*x), vps::tv<__nv_bfloat16>(*y), W);
+  else if (y->dtype == VPS_F32) flow_deconv_kernel<__nv_bfloat16, float><<<grid, 128, 0, st>>>(vps::tv<const __nv_bfloat16>(*x), vps::tv<float>(*y), W);
+  else flow_deconv_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, st>>>(vps::tv<const __nv_bfloat16>(*x), vps::tv<__nv_bfloat16>(*y), W);
+  VPS_CUDA_LAST("flow_deconv");
   return VPS_OK;
 }

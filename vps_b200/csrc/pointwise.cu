@@ -117,10 +117,23 @@ __global__ void pool2d_kernel(vps::TV<const TI> src, vps::TV<TO> out, int k, int
   vps::stv<TO, V>(out.p + out.off(n, y, x) + c, acc);
 }
 
+// space-to-depth (block 2): y[n, Y, X, (dy*2+dx)*C + c] = x[n, 2Y+dy, 2X+dx, c]; out-of-range reads (odd sizes) are 0.
+// Turns a stride-2 convolution over C channels into a stride-1 convolution over 4C channels (first layers).
+template <typename TI, typename TO>
+__global__ void space_to_depth2_kernel(vps::TV<const TI> x, vps::TV<TO> y) {
+  VPS_PIX_COORDS(y, 1, k, X, Y, n);
+  const int C = x.c;
+  const int c = k % C, q = k / C;
+  const int iy = 2 * Y + (q >> 1), ix = 2 * X + (q & 1);
+  float v = 0.f;
+  if (q < 4 && iy < x.h && ix < x.w) v = vps::ldf<TI>(x.p + x.off(n, iy, ix) + c);
+  vps::stf<TO>(y.p + y.off(n, Y, X) + k, v);
+}
+
 // ---- GroupNorm: pass 1 = per-(n,group) sum / sumsq in double via block partials; pass 2 = apply
 template <typename TI>
 __global__ void gn_stats_kernel(vps::TV<const TI> x, int groups, double* __restrict__ stats) {
-  // grid: (chunks, groups, n)
+  // scalar fallback. grid: (chunks, groups, n)
   const int g = blockIdx.y, n = blockIdx.z;
   const int cg = x.c / groups;
   const int64_t npix = (int64_t)x.h * x.w;
@@ -147,6 +160,58 @@ __global__ void gn_stats_kernel(vps::TV<const TI> x, int groups, double* __restr
     }
   }
 }
+
+// vector path: a thread owns one 16-byte channel chunk (V channels, <= 2 groups) and strides over pixels, so a warp
+// reads whole pixels (fully coalesced); per-chunk partials are combined across the block's pixel rows in shared memory.
+// block = (C/V chunks) x (256*V/C pixel rows); grid: (pixel slices, 1, n)
+template <typename TI, int V>
+__global__ void __launch_bounds__(256) gn_stats_vec_kernel(vps::TV<const TI> x, int groups, double* __restrict__ stats) {
+  const int chunks = x.c / V;
+  const int rows = blockDim.x / chunks;
+  const int ch = threadIdx.x % chunks, row = threadIdx.x / chunks;
+  const int n = blockIdx.z;
+  const int cg = x.c / groups;
+  const int c0 = ch * V;
+  const int64_t npix = (int64_t)x.h * x.w;
+  float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};       // fp32 partials over <= a few thousand pixels, combined in double
+  double ds[2] = {0.0, 0.0}, dss[2] = {0.0, 0.0};
+  int cnt = 0;
+  if (row < rows) {
+    for (int64_t pix = (int64_t)blockIdx.x * rows + row; pix < npix; pix += (int64_t)gridDim.x * rows) {
+      float v[V];
+      vps::ldv<TI, V>(x.p + ((int64_t)n * npix + pix) * x.cs + c0, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int gi = (V > 1 && cg < V) ? (j / cg) : 0;      // cg < V only when V == 2 * cg
+        s[gi & 1] += v[j];
+        ss[gi & 1] += v[j] * v[j];
+      }
+      if (++cnt == 64) {
+        ds[0] += s[0]; ds[1] += s[1]; dss[0] += ss[0]; dss[1] += ss[1];
+        s[0] = s[1] = ss[0] = ss[1] = 0.f; cnt = 0;
+      }
+    }
+    ds[0] += s[0]; ds[1] += s[1]; dss[0] += ss[0]; dss[1] += ss[1];
+  }
+  __shared__ double sh[256][4];
+  sh[threadIdx.x][0] = ds[0]; sh[threadIdx.x][1] = dss[0]; sh[threadIdx.x][2] = ds[1]; sh[threadIdx.x][3] = dss[1];
+  __syncthreads();
+  if (row == 0) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int r = 0; r < rows; ++r) {
+      const double* p = sh[r * chunks + ch];
+      a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3];
+    }
+    const int g0 = c0 / cg;
+    atomicAdd(stats + ((int64_t)n * groups + g0) * 2, a0);
+    atomicAdd(stats + ((int64_t)n * groups + g0) * 2 + 1, a1);
+    if (cg < V) {
+      atomicAdd(stats + ((int64_t)n * groups + g0 + 1) * 2, a2);
+      atomicAdd(stats + ((int64_t)n * groups + g0 + 1) * 2 + 1, a3);
+    }
+  }
+}
+
 template <typename TI, typename TO, int V>
 __global__ void gn_apply_kernel(vps::TV<const TI> x, vps::TV<TO> y, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
@@ -356,8 +421,21 @@ extern "C" int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const flo
   int chunks = (int)((per_group + 256 * 32 - 1) / (256 * 32));
   if (chunks > 64) chunks = 64;
   if (chunks < 1) chunks = 1;
-  dim3 grid(chunks, groups, x->n);
-  VPS_DISPATCH_T(x->dtype, TI, (gn_stats_kernel<TI><<<grid, 256, 0, st>>>(vps::tv<const TI>(*x), groups, g_gn_stats)));
+  const int V = x->dtype == VPS_F32 ? 4 : 8;
+  const int cg = x->c / groups;
+  const bool vstats = vps::vec_ok(*x, x->c) && (x->c / V) <= 256 && 256 % (x->c / V) == 0 && (cg >= V ? cg % V == 0 : V == 2 * cg);
+  if (vstats) {
+    const int rows = 256 / (x->c / V);
+    int64_t slices = ((int64_t)x->h * x->w + rows * 32 - 1) / (rows * 32);
+    if (slices > 148 * 4) slices = 148 * 4;
+    if (slices < 1) slices = 1;
+    dim3 grid((unsigned)slices, 1, x->n);
+    if (x->dtype == VPS_F32) gn_stats_vec_kernel<float, 4><<<grid, 256, 0, st>>>(vps::tv<const float>(*x), groups, g_gn_stats);
+    else gn_stats_vec_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(vps::tv<const __nv_bfloat16>(*x), groups, g_gn_stats);
+  } else {
+    dim3 grid(chunks, groups, x->n);
+    VPS_DISPATCH_T(x->dtype, TI, (gn_stats_kernel<TI><<<grid, 256, 0, st>>>(vps::tv<const TI>(*x), groups, g_gn_stats)));
+  }
   VPS_CUDA_LAST("gn_stats");
   const bool vec = x->dtype == y->dtype && vps::vec_ok(*x, x->c) && vps::vec_ok(*y, x->c);
   if (vec && y->dtype == VPS_F32)
@@ -406,5 +484,15 @@ extern "C" int vps_sigmoid_flat(const vps_tensor* t, float* dst, void* stream) {
   VPS_DISPATCH_T(t->dtype, TI,
                  (sigmoid_flat_kernel_t<TI><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(vps::tv<const TI>(*t), dst, total)));
   VPS_CUDA_LAST("sigmoid_flat");
+  return VPS_OK;
+}
+
+extern "C" int vps_space_to_depth2(const vps_tensor* x, const vps_tensor* y, void* stream) {
+  VPS_CHECK_ARG(y->c == 4 * x->c && y->h == (x->h + 1) / 2 && y->w == (x->w + 1) / 2 && y->n == x->n, "space_to_depth2: shapes");
+  if (!((int64_t)y->n * y->h * y->w * y->c)) return VPS_OK;
+  DISPATCH_IO(x->dtype, y->dtype, TI, TO,
+              (space_to_depth2_kernel<TI, TO><<<vps::pix_grid(y->w, y->c, y->h, y->n), 256, 0, (cudaStream_t)stream>>>(
+                  vps::tv<const TI>(*x), vps::tv<TO>(*y))));
+  VPS_CUDA_LAST("space_to_depth2");
   return VPS_OK;
 }

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import ACT_LRELU, ACT_NONE, Conv, deconv4x4_s2, empty_nhwc
+from .layers import ACT_LRELU, ACT_NONE, Conv, StemConv7x7s2, deconv4x4_s2, empty_nhwc
 from .modules import _Prepared, _conv
 
 
@@ -42,10 +42,14 @@ class _Net(nn.Module):
         for name, m in self.named_children():
             if isinstance(m, nn.Sequential) and isinstance(m[0], nn.ConvTranspose2d):
                 self.k[name] = deconv4x4_s2(m[0].weight.detach(), None if m[0].bias is None else m[0].bias.detach())
+            elif isinstance(m, nn.Sequential) and m[0].kernel_size == (7, 7) and m[0].stride == (2, 2):
+                self.k[name] = StemConv7x7s2(m[0].weight.detach(), m[0].bias.detach(), act=ACT_LRELU)
             elif isinstance(m, nn.Sequential):
                 self.k[name] = _conv(m[0], act=ACT_LRELU if len(m) > 1 else ACT_NONE)
-            elif isinstance(m, nn.ConvTranspose2d):
-                self.k[name] = deconv4x4_s2(m.weight.detach(), None if m.bias is None else m.bias.detach())
+            elif isinstance(m, nn.ConvTranspose2d):      # 2->2 flow up-sampler: dedicated kernel, weights as arguments
+                wl = m.weight.detach().float().cpu().reshape(-1).tolist()
+                bl = None if m.bias is None else m.bias.detach().float().cpu().tolist()
+                self.k[name] = (lambda x, y, wl=wl, bl=bl: ops.flow_deconv(x, wl, bl, y))
             elif isinstance(m, nn.Conv2d):
                 self.k[name] = _conv(m)
 

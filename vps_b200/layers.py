@@ -29,25 +29,8 @@ class Conv:
                 (w + 2 * self.pad - self.pk.kw) // self.stride + 1)
 
     def tc_ok(self, x):
-        # tensor-core path needs bf16, 16-byte aligned pixel stride and enough K to be worth a 64-wide chunk
-        return (x.dtype == torch.bfloat16 and self.cin >= 16 and ops.vt(x).cs % 8 == 0
-                and x.data_ptr() % 16 == 0)
-
-    def _small_cin_tc(self):
-        """bf16 + tiny cin (3..15 channels, first layers): explicit im2col to a K-padded matrix, then the
-        tensor-core kernel runs it as a 1x1 conv.  Weight columns follow vps_im2col: k = (r*kw+s)*cin + ci."""
-        if not hasattr(self, "_pk_cols"):
-            w = self.pk.weight
-            if self.pk.scale is not None:
-                w = w * self.pk.scale.view(-1, 1, 1, 1)
-            co, ci, kh, kw = w.shape
-            kk = kh * kw * ci
-            kpad = (kk + 63) // 64 * 64
-            w2 = torch.zeros(co, kpad, 1, 1, dtype=torch.float32, device=w.device)
-            w2[:, :kk, 0, 0] = w.permute(0, 2, 3, 1).reshape(co, kk)
-            self._pk_cols = PackedConv(w2, self.pk.bias)
-            self._kpad = kpad
-        return self._pk_cols, self._kpad
+        # tensor-core path: bf16 activations with a 16-byte aligned base and pixel stride (TMA requirement)
+        return x.dtype == torch.bfloat16 and ops.vt(x).cs % 8 == 0 and x.data_ptr() % 16 == 0
 
     def __call__(self, x, y=None, act=None, res=None, res_after_act=False, out_scale=1.0, out_dtype=None):
         n, h, w, _ = x.shape
@@ -55,16 +38,48 @@ class Conv:
         if y is None:
             y = empty_nhwc(n, oh, ow, self.cout, out_dtype or x.dtype, x.device)
         act = self.act if act is None else act
-        if x.dtype == torch.bfloat16 and self.cin < 16 and self.pk.kh * self.pk.kw > 1:
-            pk, kpad = self._small_cin_tc()
-            cols = torch.empty(n, oh, ow, kpad, dtype=torch.bfloat16, device=x.device)
-            ops.im2col(x, cols, self.pk.kh, self.pk.kw, self.stride, self.stride, self.pad, self.pad)
-            ops.conv2d(cols, pk, y, act=act, slope=self.slope, res=res, res_after_act=res_after_act,
-                       out_scale=out_scale, use_tc=True)
-            return y
+        if x.dtype == torch.bfloat16 and not self.tc_ok(x):
+            # mis-aligned channel slice (e.g. frame 2 of the 6-channel FlowNet input): re-base it once
+            xa = empty_nhwc(n, h, w, x.shape[3], x.dtype, x.device)
+            ops.copy_scale(x, xa)
+            x = xa
         ops.conv2d(x, self.pk, y, stride=self.stride, pad=self.pad, act=act,
                    slope=self.slope, res=res, res_after_act=res_after_act, out_scale=out_scale,
                    use_tc=self.tc_ok(x))
+        return y
+
+
+class StemConv7x7s2:
+    """nn.Conv2d(cin, cout, 7, stride=2, padding=3) for thin inputs (ResNet / FlowNetC / FlowNetS conv1).
+
+    bf16: space-to-depth(2) turns it into a 4x4 stride-1 convolution over 4*cin channels, which the tensor-core
+    kernel runs with unit-stride TMA rows (a stride-2 box over 3..12 channels would be a slow element gather):
+        in row 2*oy - 3 + r,  r' = r + 1  ->  block row I = oy - 2 + r'//2, parity dy = r' % 2
+        W'[co, (dy*2+dx)*cin + c, R, S] = W[co, c, 2R+dy-1, 2S+dx-1]   (0 where an index is -1), padding 2.
+    fp32 (parity mode): the plain 7x7 stride-2 CUDA-core convolution."""
+
+    def __init__(self, weight, bias=None, act=ACT_NONE, slope=0.1, scale=None):
+        self.plain = Conv(weight, bias, stride=2, pad=3, act=act, slope=slope, scale=scale)
+        w = weight if scale is None else weight * scale.view(-1, 1, 1, 1)
+        co, ci, _, _ = w.shape
+        wp = torch.zeros(co, ci, 8, 8, dtype=torch.float32, device=w.device)
+        wp[:, :, 1:, 1:] = w                                   # index r' = r + 1
+        w2 = wp.view(co, ci, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4).reshape(co, 4 * ci, 4, 4).contiguous()
+        self.s2d = Conv(w2, bias, stride=1, pad=2, act=act, slope=slope)
+        self.cin, self.cout, self.act = ci, co, act
+
+    def __call__(self, x, y=None, act=None, out_dtype=None):
+        if x.dtype != torch.bfloat16:
+            return self.plain(x, y, act=act, out_dtype=out_dtype)
+        n, h, w, c = x.shape
+        xs = empty_nhwc(n, (h + 1) // 2, (w + 1) // 2, 4 * c, x.dtype, x.device)
+        ops.space_to_depth2(x, xs)
+        oh, ow = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+        if y is None:
+            y = empty_nhwc(n, oh, ow, self.cout, out_dtype or x.dtype, x.device)
+        # the 4x4/pad-2 conv yields (h/2 + 1) rows; the stride-2 conv defines only the first oh x ow of them
+        ops.conv2d(xs, self.s2d.pk, y, stride=1, pad=2, act=self.act if act is None else act, slope=self.s2d.slope,
+                   oh=oh, ow=ow, use_tc=True)
         return y
 
 
@@ -93,9 +108,14 @@ class _PhaseDeconv:
         n, h, w, _ = x.shape
         use_tc = (x.dtype == torch.bfloat16 and self.cin >= 16 and ops.vt(x).cs % 8 == 0
                   and x.data_ptr() % 16 == 0)
+        if use_tc:      # all four stride phases in one persistent launch
+            ops.conv2d_tc_multi(x, [ph[3] for ph in self.phases], y, [ph[2] for ph in self.phases],
+                                [(2, ph[0], 2, ph[1]) for ph in self.phases], act=act, slope=slope,
+                                out_scale=out_scale, oh=h, ow=w)
+            return y
         for py, px, pad, pk in self.phases:
             ops.conv2d(x, pk, y, stride=1, pad_hw=pad, act=act, slope=slope, oh=h, ow=w,
-                       omap=(2, py, 2, px), out_scale=out_scale, use_tc=use_tc)
+                       omap=(2, py, 2, px), out_scale=out_scale, use_tc=False)
         return y
 
 

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import (ACT_LRELU, ACT_NONE, ACT_RELU, Conv, Linear, deconv2x2_s2, deconv4x4_s2, empty_nhwc)
+from .layers import (ACT_LRELU, ACT_NONE, ACT_RELU, Conv, Linear, StemConv7x7s2, deconv2x2_s2, deconv4x4_s2, empty_nhwc)
 from .registry import (BACKBONES, EXTRA_NECKS, HEADS, LOSSES, NECKS, PANOPTIC, ROI_EXTRACTORS, build_loss)
 
 
@@ -131,7 +131,8 @@ class ResNet(_Prepared):
             setattr(self, 'layer%d' % (i + 1), nn.Sequential(*layers))
 
     def _pack(self):
-        self.k_stem = _conv(self.conv1, act=ACT_RELU, bn=self.bn1)
+        sc, sh = _bn_fold(self.bn1)
+        self.k_stem = StemConv7x7s2(self.conv1.weight.detach(), sh.detach(), act=ACT_RELU, scale=sc.detach())
         self.k_layers = []
         for i in range(self.num_stages):
             blocks = []

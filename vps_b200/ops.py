@@ -93,17 +93,22 @@ class PackedConv:
         self.weight = weight.contiguous().float()
         self.scale = scale.contiguous().float() if scale is not None else None
         self.bias = bias.contiguous().float() if bias is not None else None
-        self._tc = None
+        self._tc = {}
         self._simt = None
 
-    def tc(self):
-        if self._tc is None:
-            nbytes = lib().vps_packed_tc_bytes(self.cout, self.cin, self.kh, self.kw)
+    def gran(self):
+        """channel granularity of the tensor-core K step (16 or 64)."""
+        return 16 if self.cin <= 16 else 64     # thin stems only: bk=16 multiplies the number of (tiny) K steps
+
+    def tc(self, gran=None):
+        gran = gran or self.gran()
+        if gran not in self._tc:
+            nbytes = lib().vps_packed_tc_bytes(self.cout, self.cin, self.kh, self.kw, gran)
             buf = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=self.weight.device)
             check(lib().vps_pack_weights_tc(_ptr(self.weight), _ptr(self.scale), _ptr(buf), self.cout, self.cin,
-                                            self.kh, self.kw, int(self.transposed), stream()), "pack_weights_tc")
-            self._tc = buf
-        return self._tc
+                                            self.kh, self.kw, int(self.transposed), gran, stream()), "pack_weights_tc")
+            self._tc[gran] = buf
+        return self._tc[gran]
 
     def simt(self):
         if self._simt is None:
@@ -116,12 +121,10 @@ class PackedConv:
         return self._simt
 
 
-def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_after_act=False, out_scale=1.0,
-           oh=None, ow=None, omap=(1, 0, 1, 0), pad_hw=None, use_tc=None, w_override=None, khw=None):
-    """y <- conv(x) with fused bias/activation/residual.  `omap` = (oy_mul, oy_off, ox_mul, ox_off)."""
+def _conv_args(x, pw, y, stride, pad, act, slope, res, res_after_act, out_scale, oh, ow, omap, pad_hw):
     a = VpsConvArgs()
     a.x, a.y, a.res = vt(x), vt(y), vt(res)
-    kh, kw = khw if khw is not None else (pw.kh, pw.kw)
+    kh, kw = pw.kh, pw.kw
     sh, sw = (stride, stride) if isinstance(stride, int) else stride
     ph, pw_ = pad_hw if pad_hw is not None else ((pad, pad) if isinstance(pad, int) else pad)
     a.kh, a.kw, a.sh, a.sw, a.ph, a.pw = kh, kw, sh, sw, ph, pw_
@@ -133,23 +136,55 @@ def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_aft
     a.cin, a.cout = pw.cin, pw.cout
     a.act, a.slope, a.res_after_act, a.out_scale = act, slope, int(res_after_act), out_scale
     a.bias = pw.bias.data_ptr() if pw.bias is not None else None
+    return a
+
+
+def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_after_act=False, out_scale=1.0,
+           oh=None, ow=None, omap=(1, 0, 1, 0), pad_hw=None, use_tc=None):
+    """y <- conv(x) with fused bias/activation/residual.  `omap` = (oy_mul, oy_off, ox_mul, ox_off)."""
+    a = _conv_args(x, pw, y, stride, pad, act, slope, res, res_after_act, out_scale, oh, ow, omap, pad_hw)
     if use_tc is None:
         use_tc = x.dtype == torch.bfloat16
     if PROFILE is not None:
-        _NOTE["flops"] = 2 * x.shape[0] * oh * ow * pw.cout * pw.cin * kh * kw
-        _NOTE["tag"] = "%dx%d s%d %d->%d @%dx%d" % (kh, kw, sh, pw.cin, pw.cout, oh, ow)
+        _NOTE["flops"] = 2 * x.shape[0] * a.oh * a.ow * pw.cout * pw.cin * a.kh * a.kw
+        _NOTE["tag"] = "%dx%d s%d %d->%d @%dx%d" % (a.kh, a.kw, a.sh, pw.cin, pw.cout, a.oh, a.ow)
     if use_tc:
-        a.w = (w_override if w_override is not None else pw.tc()).data_ptr()
+        a.cin_gran = pw.gran()
+        a.w = pw.tc().data_ptr()
         check(lib().vps_conv2d_tc(C.byref(a), stream()), "conv2d_tc")
     else:
-        a.w = (w_override if w_override is not None else pw.simt()).data_ptr()
+        a.w = pw.simt().data_ptr()
         check(lib().vps_conv2d_simt(C.byref(a), stream()), "conv2d_simt")
     return y
 
 
+def conv2d_tc_multi(x, pws, y, pads, omaps, act=ACT_NONE, slope=0.1, out_scale=1.0, oh=None, ow=None):
+    """Up to 4 sub-convolutions (same input / output tensors, stride 1) in one persistent tensor-core launch:
+    the stride phases of a transposed convolution."""
+    n = len(pws)
+    arr = (VpsConvArgs * n)()
+    gran = pws[0].gran()
+    for i in range(n):
+        a = _conv_args(x, pws[i], y, 1, 0, act, slope, None, False, out_scale, oh, ow, omaps[i], pads[i])
+        a.cin_gran = gran
+        a.w = pws[i].tc(gran).data_ptr()
+        arr[i] = a
+    if PROFILE is not None:
+        _NOTE["flops"] = 2 * x.shape[0] * arr[0].oh * arr[0].ow * pws[0].cout * pws[0].cin * arr[0].kh * arr[0].kw * n
+        _NOTE["tag"] = "%dx%d x%d phases %d->%d @%dx%d" % (arr[0].kh, arr[0].kw, n, pws[0].cin, pws[0].cout, arr[0].oh, arr[0].ow)
+    check(lib().vps_conv2d_tc_multi(arr, n, stream()), "conv2d_tc_multi")
+    return y
+
+
 # ------------------------------------------------------------------ FlowNet2 native ops
-def correlation(f1, f2, out, pad, max_disp, stride1, stride2, act=ACT_NONE, slope=0.1):
-    check(lib().vps_correlation(C.byref(vt(f1)), C.byref(vt(f2)), C.byref(vt(out)), pad, max_disp, stride1,
+def correlation(f1, f2, out, pad, max_disp, stride1, stride2, act=ACT_NONE, slope=0.1, impl=None):
+    """impl: None = dispatch (tensor cores for bf16 features), "tc" / "simt" force one implementation."""
+    fn = {None: "vps_correlation", "tc": "vps_correlation_tc", "simt": "vps_correlation_simt"}[impl]
+    if PROFILE is not None:
+        d = 2 * (max_disp // stride2) + 1
+        _NOTE["flops"] = 2 * f1.shape[0] * f1.shape[1] * f1.shape[2] * f1.shape[3] * d * d
+        _NOTE["tag"] = "corr d%d s%d C%d @%dx%d" % (max_disp, stride2, f1.shape[3], f1.shape[1], f1.shape[2])
+    check(getattr(lib(), fn)(C.byref(vt(f1)), C.byref(vt(f2)), C.byref(vt(out)), pad, max_disp, stride1,
                                 stride2, act, C.c_float(slope), stream()), "correlation")
     return out
 
@@ -364,3 +399,16 @@ def track_update(mem_feats, det_feats, feat_len, mem_boxes, det_boxes, mem_label
 
 def det_split(det_rois, cls_idx, cap, boxes, labels):
     check(lib().vps_det_split(_ptr(det_rois), _ptr(cls_idx), cap, _ptr(boxes), _ptr(labels), stream()), "det_split")
+
+
+def flow_deconv(x, w_host, b_host, y):
+    """x [n,h,w,2] -> y [n,2h,2w,2]; w_host: 64 python floats (IOHW), b_host: 2 floats or None."""
+    w = (C.c_float * 64)(*w_host)
+    b = (C.c_float * 2)(*b_host) if b_host is not None else None
+    check(lib().vps_flow_deconv(_bt(x), w, b, _bt(y), stream()), "flow_deconv")
+    return y
+
+
+def space_to_depth2(x, y):
+    check(lib().vps_space_to_depth2(_bt(x), _bt(y), stream()), "space_to_depth2")
+    return y
