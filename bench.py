@@ -235,10 +235,13 @@ def run_gpu_arm(args):
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)) or ".", exist_ok=True)
             with open(args.profile_out, "w") as f:
-                for name, s, e, fl, tag in rec[len(rec) // 2:]:
-                    f.write(json.dumps({"fn": name, "ms": s.elapsed_time(e), "flops": fl, "tag": tag}) + "\n")
-        agg = {}
-        for name, s, e, fl, tag in rec:
+                for name, s, e, fl, tag, scope in rec[len(rec) // 2:]:
+                    f.write(json.dumps({"fn": name, "ms": s.elapsed_time(e), "flops": fl, "tag": tag, "scope": scope}) + "\n")
+        agg, scopes = {}, {}
+        for name, s, e, fl, tag, scope in rec:
+            sc = scopes.setdefault(scope, [0.0, 0.0])
+            sc[0] += s.elapsed_time(e) / 2; sc[1] += fl / 2
+        for name, s, e, fl, tag, scope in rec:
             a = agg.setdefault(name, [0.0, 0.0, 0])
             a[0] += s.elapsed_time(e); a[1] += fl; a[2] += 1
         tc_ms, tc_fl, tc_n = agg.get("vps_conv2d_tc", [0.0, 0.0, 0])
@@ -272,6 +275,13 @@ def run_gpu_arm(args):
             line["roofline"] = roof
         if breakdown:
             line["breakdown"] = breakdown
+            line["stages"] = {k: {"ms": round(v[0], 3), "gflop": round(v[1] / 1e9, 1)} for k, v in scopes.items()}
+            if "r50fpn" in scopes:      # north-star target: fraction of the conv-FLOP roofline on 2 x ResNet-50-FPN
+                t = scopes["r50fpn"][0] * 1e-3
+                ach = GFLOP_R50FPN_PAIR * (H * W) / float(H_FULL * W_FULL) * 1e9 / t / 1e12
+                line["r50fpn_roofline"] = {"achieved": ach, "peak": peaks()["tf_sus"], "unit": "TFLOP/s",
+                                           "frac": ach / peaks()["tf_sus"], "ms": scopes["r50fpn"][0],
+                                           "note": "eager instrumented step (CUDA events per call), algorithmic 1158.4 GFLOP/pair"}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

@@ -150,10 +150,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): a 32-column chunk of a pixel is 2 (bf16) or 4 (fp32) of them
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]),
+               "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
 // ---------------------------------------------------------------- epilogue math for one 32-column chunk of one pixel
 template <int ACT>
-__device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t (&r)[32], int64_t pix, int n0) {
-  const int nv = min(32, p.cout - n0);
+__device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t (&r)[32], int64_t pix, int n0, int nlim) {
+  const int nv = min(32, nlim - n0);      // nlim = end of this tile's channel range (N tiles may be narrower than 32)
   const bool full = nv == 32;
   float v[32];
 #pragma unroll
@@ -178,7 +188,18 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
     const int64_t ro = pix * p.res_cs + n0;
     if (p.res_dtype == VPS_BF16) {
       const __nv_bfloat16* rp = (const __nv_bfloat16*)p.res + ro;
-      if (full && p.res_vec) {
+      if (full && p.res_vec == 2) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t raw[8];
+          ld_global_256(rp + 16 * j, raw);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[t]));
+            v[16 * j + 2 * t] += f.x; v[16 * j + 2 * t + 1] += f.y;
+          }
+        }
+      } else if (full && p.res_vec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 raw = *reinterpret_cast<const uint4*>(rp + 8 * j);
@@ -214,7 +235,18 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
   const int64_t yo = pix * p.y_cs + n0;
   if (p.y_dtype == VPS_BF16) {
     __nv_bfloat16* yp = (__nv_bfloat16*)p.y + yo;
-    if (p.y_vec && full) {
+    if (p.y_vec == 2 && full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 16) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+          pk[t] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        st_global_256(yp + j, pk);
+      }
+    } else if (p.y_vec && full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 pk;
@@ -232,7 +264,15 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
     }
   } else {
     float* yp = (float*)p.y + yo;
-    if (p.y_vec && full) {
+    if (p.y_vec == 2 && full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pk[t] = __float_as_uint(v[j + t]);
+        st_global_256(yp + j, pk);
+      }
+    } else if (p.y_vec && full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *(float4*)(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
@@ -268,6 +308,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
     const bool valid = (oy < p.oh) && (ox < p.ow);
     const int64_t pix = ((int64_t)img * p.y_h + (oy * p.oy_mul + p.oy_off_[prob])) * p.y_w + (ox * p.ox_mul + p.ox_off_[prob]);
     const int nbase = n_idx * p.block_n;
+    const int nlim = min(p.cout, nbase + p.block_n);
 
     mbar_wait(tfull0 + 8u * acc, acc_phase);
     tc_fence_after();
@@ -279,12 +320,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
       tmem_ld_wait();
       const int c1 = c0 + 64;
       if (c1 < p.block_n) tmem_ld32(t_row + (uint32_t)c1, rb);
-      if (valid && nbase + c0 < p.cout) epi_chunk<ACT>(p, ra, pix, nbase + c0);
+      if (valid && nbase + c0 < nlim) epi_chunk<ACT>(p, ra, pix, nbase + c0, nlim);
       if (c1 >= p.block_n) break;
       tmem_ld_wait();
       const int c2 = c1 + 64;
       if (c2 < p.block_n) tmem_ld32(t_row + (uint32_t)c2, ra);
-      if (valid && nbase + c1 < p.cout) epi_chunk<ACT>(p, rb, pix, nbase + c1);
+      if (valid && nbase + c1 < nlim) epi_chunk<ACT>(p, rb, pix, nbase + c1, nlim);
       c0 = c2;
     }
     tmem_ld_wait();
@@ -564,6 +605,7 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
   p.y = a->y.ptr; p.y_h = a->y.h; p.y_w = a->y.w; p.y_cs = a->y.cs; p.y_dtype = a->y.dtype;
   const int esz = a->y.dtype == VPS_BF16 ? 2 : 4;
   p.y_vec = (((uintptr_t)a->y.ptr & 15) == 0) && ((a->y.cs * esz) % 16 == 0);
+  if (p.y_vec && (((uintptr_t)a->y.ptr & 31) == 0) && ((a->y.cs * esz) % 32 == 0)) p.y_vec = 2;     // 256-bit stores
   p.oy_mul = a->oy_mul; p.ox_mul = a->ox_mul;
   for (int i = 0; i < MAX_PROB; ++i) {
     const vps_conv_args* q = &args[i < nprob ? i : 0];
@@ -573,6 +615,7 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
   }
   p.res = a->res.ptr; p.res_cs = a->res.cs; p.res_dtype = a->res.dtype; p.res_after_act = a->res_after_act;
   p.res_vec = a->res.ptr && (((uintptr_t)a->res.ptr & 15) == 0) && (a->res.cs % 8 == 0);
+  if (p.res_vec && (((uintptr_t)a->res.ptr & 31) == 0) && (a->res.cs % 16 == 0)) p.res_vec = 2;       // 256-bit loads
   VPS_CHECK_ARG(!a->bias || ((uintptr_t)a->bias & 15) == 0, "conv2d_tc: bias must be 16-byte aligned");
   p.bias = a->bias; p.cout = a->cout; p.act = a->act; p.slope = a->slope; p.out_scale = a->out_scale;
   if (a->res.ptr) VPS_CHECK_ARG(a->res.h == a->y.h && a->res.w == a->y.w, "conv2d_tc: residual geometry");

@@ -14,7 +14,7 @@
 //
 //   warp 0: TMA producer (f1 tile resident & double-buffered per tile; f2 blocks streamed through a 6-stage ring)
 //   warp 1: TMEM alloc + tcgen05.mma issue (M=128, N=96, K=16), accumulators double-buffered
-//   warps 2-5: epilogue, warp q = neighbourhood row 4*block + q
+//   warps 2-9: epilogue, warp -> neighbourhood row 4*block + (warp % 4); the two warps of a row split the output rows
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -106,7 +106,7 @@ __device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.syn
 
 // R = max_displacement / stride2, S2 = stride2.  TW = 32 - 2R so the neighbourhood is exactly 32 columns wide.
 template <int R, int S2>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2, const CorrParams p) {
   constexpr int D = 2 * R + 1;
   constexpr int TW = 32 - 2 * R;
@@ -130,7 +130,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); mbar_init(tfull(s), 1); mbar_init(tempty(s), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -211,9 +211,16 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__
       }
     }
   } else {
-    const int q = warp & 3;              // TMEM lane quarter = neighbourhood row inside the block
+    // 8 epilogue warps: warp -> TMEM lane quarter q (= neighbourhood row inside the block); the two warps of a quarter
+    // take alternate output rows i.  The TMEM load of the next row is in flight while the current one is stored.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0; uint32_t aphase = 0;
     const float inv_c = 1.0f / (float)p.C;
+    auto load_row = [&](uint32_t t_row, int i, uint32_t* r) {
+      if constexpr (TW == 12) { tmem_ld<8>(t_row + i * TW, r); tmem_ld<4>(t_row + i * TW + 8, r + 8); }
+      else { tmem_ld<16>(t_row + i * TW, r); tmem_ld<8>(t_row + i * TW + 16, r + 16); }
+    };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int img, py, px, y0, x0;
       decode(tile, img, py, px, y0, x0);
@@ -222,30 +229,41 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__
         tc_fence_after();
         const int ip = 4 * b + q;        // neighbourhood row i' of this warp; lane = neighbourhood column j'
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
-        // output rows i with 0 <= i' - i < D
-        const int i_lo = max(0, ip - D + 1), i_hi = min(TH - 1, ip);
-        for (int i = i_lo; i <= i_hi; ++i) {
+        // output rows i with 0 <= i' - i < D, split between the two warps of this quarter
+        const int i_lo = max(0, ip - D + 1) + half, i_hi = min(TH - 1, ip);
+        auto store_row = [&](int i, const uint32_t* r) {
           const int tj = ip - i;
           const int y = y0 + py + i * S2;
-          uint32_t r[TW];
-          if constexpr (TW == 12) { tmem_ld<8>(t_row + i * TW, r); tmem_ld<4>(t_row + i * TW + 8, r + 8); }
-          else { tmem_ld<16>(t_row + i * TW, r); tmem_ld<8>(t_row + i * TW + 16, r + 16); }
-          tmem_wait();
-          if (y < p.H) {
+          if (y >= p.H) return;
+          const int64_t rowb = ((int64_t)img * p.H + y) * p.W * p.out_cs + tj * D + lane;
 #pragma unroll
-            for (int j = 0; j < TW; ++j) {
-              const int ti = lane - j;
-              const int x = x0 + px + j * S2;
-              if (ti >= 0 && ti < D && x < p.W) {
-                float v = __uint_as_float(r[j]) * inv_c;
-                if (p.act == VPS_ACT_LRELU) v = v > 0.f ? v : v * p.slope;
-                const int64_t o = (((int64_t)img * p.H + y) * p.W + x) * p.out_cs + tj * D + ti;
-                if (p.out_dtype == VPS_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(v);
-                else ((float*)p.out)[o] = v;
-              }
+          for (int j = 0; j < TW; ++j) {
+            const int ti = lane - j;
+            const int x = x0 + px + j * S2;
+            if (ti >= 0 && ti < D && x < p.W) {
+              float v = __uint_as_float(r[j]) * inv_c;
+              if (p.act == VPS_ACT_LRELU) v = v > 0.f ? v : v * p.slope;
+              const int64_t o = rowb + (int64_t)x * p.out_cs - j;
+              if (p.out_dtype == VPS_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(v);
+              else ((float*)p.out)[o] = v;
             }
           }
+        };
+        uint32_t ra[TW], rb[TW];
+        int i = i_lo;
+        if (i <= i_hi) load_row(t_row, i, ra);
+        while (i <= i_hi) {
+          tmem_wait();
+          if (i + 2 <= i_hi) load_row(t_row, i + 2, rb);
+          store_row(i, ra);
+          i += 2;
+          if (i > i_hi) break;
+          tmem_wait();
+          if (i + 2 <= i_hi) load_row(t_row, i + 2, ra);
+          store_row(i, rb);
+          i += 2;
         }
+        tmem_wait();
         tc_fence_before();
         mbar_arrive(tempty(acc));
         acc ^= 1; if (acc == 0) aphase ^= 1;
@@ -313,7 +331,7 @@ int launch(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, in
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, 192, smem, st>>>(tm1, tm2, p);
+  kern<<<grid, 320, smem, st>>>(tm1, tm2, p);
   VPS_CUDA_LAST("corr_tc_kernel");
   return VPS_OK;
 }

@@ -104,31 +104,33 @@ int launch_corr(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* ou
 }
 
 // ------------------------------------------------------------------ resample2d
-template <typename T, typename TF>
-__global__ void resample2d_kernel(vps::TV<const T> src, vps::TV<const TF> flow, vps::TV<T> out, int64_t total) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % out.c);
-    int64_t t = i / out.c;
-    const int x = (int)(t % out.w); t /= out.w;
-    const int y = (int)(t % out.h);
-    const int n = (int)(t / out.h);
-    const TF* fp = flow.p + flow.off(n, y, x);
-    const float dx = vps::ldf<TF>(fp), dy = vps::ldf<TF>(fp + 1);
-    const float xf = (float)x + dx, yf = (float)y + dy;
-    const float alpha = xf - floorf(xf), beta = yf - floorf(yf);
-    // border clamp of the tap coordinates, fractional weights NOT renormalised (resample2d_kernel.cu:44-52)
-    const int xL = max(min((int)floorf(xf), src.w - 1), 0);
-    const int xR = max(min((int)floorf(xf) + 1, src.w - 1), 0);
-    const int yT = max(min((int)floorf(yf), src.h - 1), 0);
-    const int yB = max(min((int)floorf(yf) + 1, src.h - 1), 0);
+template <typename T, typename TF, int V>
+__global__ void resample2d_kernel(vps::TV<const T> src, vps::TV<const TF> flow, vps::TV<T> out) {
+  VPS_PIX_COORDS(out, V, c, x, y, n);
+  const TF* fp = flow.p + flow.off(n, y, x);
+  const float dx = vps::ldf<TF>(fp), dy = vps::ldf<TF>(fp + 1);
+  const float xf = (float)x + dx, yf = (float)y + dy;
+  const float alpha = xf - floorf(xf), beta = yf - floorf(yf);
+  // border clamp of the tap coordinates, fractional weights NOT renormalised (resample2d_kernel.cu:44-52)
+  const int xL = max(min((int)floorf(xf), src.w - 1), 0);
+  const int xR = max(min((int)floorf(xf) + 1, src.w - 1), 0);
+  const int yT = max(min((int)floorf(yf), src.h - 1), 0);
+  const int yB = max(min((int)floorf(yf) + 1, src.h - 1), 0);
+  float a[V], b[V], cc[V], d[V];
+  vps::ldv<T, V>(src.p + src.off(n, yT, xL) + c, a);
+  vps::ldv<T, V>(src.p + src.off(n, yT, xR) + c, b);
+  vps::ldv<T, V>(src.p + src.off(n, yB, xL) + c, cc);
+  vps::ldv<T, V>(src.p + src.off(n, yB, xR) + c, d);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
     float v = 0.f;
-    v += (1.f - alpha) * (1.f - beta) * vps::ldf<T>(src.p + src.off(n, yT, xL) + c);
-    v += (alpha) * (1.f - beta) * vps::ldf<T>(src.p + src.off(n, yT, xR) + c);
-    v += (1.f - alpha) * (beta) * vps::ldf<T>(src.p + src.off(n, yB, xL) + c);
-    v += (alpha) * (beta) * vps::ldf<T>(src.p + src.off(n, yB, xR) + c);
-    vps::stf<T>(out.p + out.off(n, y, x) + c, v);
+    v += (1.f - alpha) * (1.f - beta) * a[j];
+    v += (alpha) * (1.f - beta) * b[j];
+    v += (1.f - alpha) * (beta) * cc[j];
+    v += (alpha) * (beta) * d[j];
+    a[j] = v;
   }
+  vps::stv<T, V>(out.p + out.off(n, y, x) + c, a);
 }
 
 // ------------------------------------------------------------------ channelnorm
@@ -199,19 +201,20 @@ extern "C" int vps_correlation_simt(const vps_tensor* f1, const vps_tensor* f2, 
 extern "C" int vps_resample2d(const vps_tensor* src, const vps_tensor* flow, const vps_tensor* out, void* stream) {
   VPS_CHECK_ARG(src->dtype == out->dtype && src->c == out->c && flow->c >= 2, "resample2d: bad args");
   VPS_CHECK_ARG(flow->h == out->h && flow->w == out->w, "resample2d: flow/out size");
-  const int64_t total = (int64_t)out->n * out->h * out->w * out->c;
-  if (!total) return VPS_OK;
+  if (!((int64_t)out->n * out->h * out->w * out->c)) return VPS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int g = grid_for(total, 256);
-  VPS_DISPATCH_T(src->dtype, T, {
-    if (flow->dtype == VPS_F32)
-      resample2d_kernel<T, float><<<g, 256, 0, st>>>(vps::tv<const T>(*src), vps::tv<const float>(*flow),
-                                                    vps::tv<T>(*out), total);
-    else
-      resample2d_kernel<T, __nv_bfloat16><<<g, 256, 0, st>>>(vps::tv<const T>(*src),
-                                                            vps::tv<const __nv_bfloat16>(*flow),
-                                                            vps::tv<T>(*out), total);
-  });
+  const bool vec = vps::vec_ok(*src, out->c) && vps::vec_ok(*out, out->c);
+#define RS_LAUNCH(T, TF, V)                                                                               \
+  resample2d_kernel<T, TF, V><<<vps::pix_grid(out->w, out->c / V, out->h, out->n), 256, 0, st>>>(          \
+      vps::tv<const T>(*src), vps::tv<const TF>(*flow), vps::tv<T>(*out))
+  if (out->dtype == VPS_F32) {
+    if (flow->dtype == VPS_F32) { if (vec) RS_LAUNCH(float, float, 4); else RS_LAUNCH(float, float, 1); }
+    else { if (vec) RS_LAUNCH(float, __nv_bfloat16, 4); else RS_LAUNCH(float, __nv_bfloat16, 1); }
+  } else {
+    if (flow->dtype == VPS_F32) { if (vec) RS_LAUNCH(__nv_bfloat16, float, 8); else RS_LAUNCH(__nv_bfloat16, float, 1); }
+    else { if (vec) RS_LAUNCH(__nv_bfloat16, __nv_bfloat16, 8); else RS_LAUNCH(__nv_bfloat16, __nv_bfloat16, 1); }
+  }
+#undef RS_LAUNCH
   VPS_CUDA_LAST("resample2d_kernel");
   return VPS_OK;
 }

@@ -182,21 +182,27 @@ class PanopticFuseTrack(nn.Module):
         dev = img.device
         _, _, H, W = img.shape
         dt = self.act_dtype
+        ops.SCOPE[0] = 'flownet2'
         flow = self.compute_flow(img, ref_img, 0.25, taps)
+        ops.SCOPE[0] = 'r50fpn'
         x_in = empty_nhwc(1, H, W, 3, dt, dev)
         r_in = empty_nhwc(1, H, W, 3, dt, dev)
         ops.nchw_to_nhwc(img, x_in)
         ops.nchw_to_nhwc(ref_img, r_in)
         x = self.extract_feat(x_in)
         ref_x = self.extract_feat(r_in)
+        ops.SCOPE[0] = 'bfp_tcea'
         xf = self.extra_neck(x, ref_x, flow, taps)
+        ops.SCOPE[0] = 'upsnet_fpn'
         nl = self.panopticFPN.num_levels
         fcn_output, fcn_score = self.panopticFPN(xf[0:nl], want_full=taps is not None)
+        ops.SCOPE[0] = 'rpn'
         # RPN (test_mixins.py:13-17, rpn_head.py:55-104)
         heads = self.rpn_head(xf)
         proposals_t, rois, nprop = self.rpn_head.get_bboxes(heads, img_shape, self.test_cfg['rpn'], taps)
         nroi = proposals_t.shape[0]
         # bbox head + MaskROI (:367-389)
+        ops.SCOPE[0] = 'bbox_head'
         roi_feats = self.bbox_roi_extractor(xf, rois, nroi, nprop)
         cls_score, bbox_pred, _ = self.bbox_head(roi_feats)
         det_rois, cls_idx, cls_prob, kout = self._mask_roi(rois, cls_score, bbox_pred, nroi, nprop, float(H), float(W))
@@ -255,6 +261,7 @@ class PanopticFuseTrack(nn.Module):
         heads, proposals_t, rois, nprop = st['heads'], st['proposals'], st['rois'], st['nprop']
         roi_feats, cls_score, bbox_pred = st['roi_feats'], st['cls_score'], st['bbox_pred']
         det_rois, cls_idx, cls_prob, kout = st['det_rois'], st['cls_idx'], st['cls_prob'], st['kout']
+        ops.SCOPE[0] = 'track_mask_fuse'
         k, dummy = [int(v) for v in kout.tolist()]            # 8-byte read-back: number of detections
         iid = meta['iid']
         is_first = (iid % 10000) == 1

@@ -18,6 +18,7 @@ _DT = {torch.float32: VPS_F32, torch.bfloat16: VPS_BF16}
 # ---- optional per-call device timing (bench.py / profiling only; off on the normal path) -----------------
 PROFILE = None        # set to a list to collect [c_function, start_event, end_event, flops, tag] per C-ABI call
 _NOTE = {"flops": 0, "tag": ""}
+SCOPE = [""]          # pipeline stage label attached to profiled calls (set by the detector)
 _real_lib = lib
 
 
@@ -32,7 +33,7 @@ class _ProfLib(object):
             s.record()
             r = f(*a)
             e.record()
-            PROFILE.append([name, s, e, _NOTE["flops"], _NOTE["tag"]])
+            PROFILE.append([name, s, e, _NOTE["flops"], _NOTE["tag"], SCOPE[0]])
             _NOTE["flops"], _NOTE["tag"] = 0, ""
             return r
         return w
