@@ -98,6 +98,12 @@ def oracle_model():
     return m
 
 
+def host_threads():
+    """threads used for the CPU arms: all cores up to 32 (beyond that torch's CPU convolutions stop scaling on the
+    small per-op work of a frame pair and oversubscription makes them slower)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def time_oracle(model, H, W, reps, threads):
     torch.set_num_threads(threads)
     pairs = synth_pairs(1, H, W, seed=3)
@@ -109,45 +115,54 @@ def time_oracle(model, H, W, reps, threads):
     return times
 
 
-def cpu_baseline(budget_s=30.0):
-    """Oracle on the host cores on a bounded sample: one frame pair at the largest size (1/16, 1/4 or full area)
-    whose predicted time fits the budget; scaled to 1024x2048-equivalent pairs/s by the area ratio (the dense
-    work is linear in pixels)."""
-    cores = os.cpu_count() or 1
+def pick_sample(model, threads, per_step_budget_s):
+    """largest sample size (64x128 ... 1024x2048) whose predicted single-pair time stays within the budget"""
+    sizes = [((64, 128), 1.0 / 256), ((128, 256), 1.0 / 64), ((256, 512), 1.0 / 16), ((512, 1024), 0.25), ((1024, 2048), 1.0)]
+    time_oracle(model, 64, 128, 1, threads)                       # warm-up (lazy inits)
+    (H0, W0), frac = sizes[0]
+    t = time_oracle(model, H0, W0, 1, threads)[0]
+    size = (H0, W0)
+    for (hh, ww), fr in sizes[1:]:
+        if t * 4 * 1.3 > per_step_budget_s:
+            break
+        t = time_oracle(model, hh, ww, 1, threads)[0]
+        size, frac = (hh, ww), fr
+    return size, frac, t
+
+
+def cpu_baseline(budget_s=15.0):
+    """Oracle on the host cores on a bounded sample: one frame pair at the largest size whose predicted time fits the
+    budget, scaled to 1024x2048-equivalent pairs/s by the area ratio (the dense work is linear in pixels; the fixed
+    per-frame head cost makes small samples slightly pessimistic for the CPU)."""
+    threads = host_threads()
     m = oracle_model()
-    t_small = min(time_oracle(m, 256, 512, 2, cores))            # 1/16 area (first call includes warm-up)
-    size, frac, t = (256, 512), 1.0 / 16, t_small
-    if t_small * 4 * 1.2 <= budget_s:
-        t4 = time_oracle(m, 512, 1024, 1, cores)[0]
-        size, frac, t = (512, 1024), 0.25, t4
-        if t4 * 4 * 1.2 <= budget_s:
-            t = time_oracle(m, 1024, 2048, 1, cores)[0]
-            size, frac = (1024, 2048), 1.0
-    return {"value": frac / t, "unit": "pairs/s (1024x2048-equivalent)", "cores": cores, "kind": "port",
+    size, frac, t = pick_sample(m, threads, budget_s)
+    return {"value": frac / t, "unit": "pairs/s (1024x2048-equivalent)", "cores": threads, "kind": "port",
             "sample": "oracle simple_test, 1 pair at %dx%d (%.3g of the 1024x2048 area) in %.2fs, scaled by area; fp32, torch CPU ops"
                       % (size[0], size[1], frac, t)}
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's own math on the host CPU.  The reference cannot execute on this stack
-    (mmcv 0.2.14 + THC extensions, hard .cuda() calls), so this is the oracle port (kind 'port')."""
+    (mmcv 0.2.14 + THC extensions, hard .cuda() calls), so this is the oracle port (kind 'port').
+    Each step = one frame pair at a bounded sample size chosen so that a step takes a few seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    threads = host_threads()
     m = oracle_model()
-    Hs, Ws = 256, 512                                # each step = 1/16 of a 1024x2048 pair's area
-    frac = (Hs * Ws) / float(H_FULL * W_FULL)
-    times = time_oracle(m, Hs, Ws, args.warmup + args.steps, cores)[args.warmup:]
+    (Hs, Ws), frac, _ = pick_sample(m, threads, per_step_budget_s=4.0)
+    times = time_oracle(m, Hs, Ws, args.warmup + args.steps, threads)[args.warmup:]
     t = float(np.mean(times))
     v = frac / t
+    sample = "each step = one %dx%d pair (%.3g of the 1024x2048 area) on %d CPU threads, scaled by area" % (Hs, Ws, frac, threads)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / frac, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FuseTrack inference, synthetic 2-frame 1024x2048 pair, random-init (synthetic set C) weights",
-                       "sample": "each step = one 256x512 pair (1/16 area) on CPU, scaled by area"},
-            "cpu_baseline": {"value": v, "unit": "pairs/s (1024x2048-equivalent)", "cores": cores, "kind": "port",
-                             "sample": "oracle simple_test, %d steps of one 256x512 pair, scaled by area" % args.steps},
+                       "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "pairs/s (1024x2048-equivalent)", "cores": threads, "kind": "port",
+                             "sample": "oracle simple_test, %d steps; %s" % (args.steps, sample)},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

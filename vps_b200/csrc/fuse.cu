@@ -2,6 +2,8 @@
 // (SegTerm unary_logits.py:81-108 + mask paste mask_removal.py:86 + argmax panoptic_fusetrack.py:588-593).
 // Neither the [1,k,H,W] mask_energy tensor nor the [1,11+k,H,W] logits tensor of the reference is
 // ever materialised: resized mask logits are recomputed from the 28x28 maps wherever they are needed.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -27,6 +29,7 @@ __device__ __forceinline__ float cv_resize_linear(const float* __restrict__ src,
   return r0 * b0 + r1 * b1;
 }
 
+constexpr int MAX_DET_K = 128;
 struct BoxI { int x1, y1, x2, y2, w, h, x_0, x_1, y_0, y_1; };
 __device__ __forceinline__ BoxI int_box(const float* b, int H, int W) {
   BoxI r;
@@ -92,6 +95,73 @@ __global__ void mr_apply_kernel(const float* __restrict__ boxes, const int32_t* 
     const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
     const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
     if (v > 0.f) oc[(int64_t)y * W + x] += 1;   // uint8 += (wraps like numpy)
+  }
+}
+
+// ---- class-parallel MaskRemoval: boxes of different classes never interact (the occupancy image is per class,
+// mask_removal.py:44,81-85), so the sequential dependence only runs along each class's score-ordered chain.
+// Step t handles the t-th box of EVERY class at once; one cooperative launch, two grid syncs per step.
+struct MrSched { int slot[8][MAX_DET_K]; int count[8]; int steps; };
+
+__global__ void mr_schedule_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ cls_idx, int k,
+                                   const int* __restrict__ k_dev, int num_things, MrSched* __restrict__ sc) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int kk = k_dev ? min(*k_dev, k) : k;
+  for (int c = 0; c < 8; ++c) sc->count[c] = 0;
+  int steps = 0;
+  for (int pos = 0; pos < kk; ++pos) {
+    const int c = cls_idx[order[pos]] - 1;
+    if (c < 0 || c >= num_things || c >= 8) continue;       // dummy / invalid class: never kept
+    sc->slot[c][sc->count[c]++] = pos;
+    steps = max(steps, sc->count[c]);
+  }
+  sc->steps = steps;
+}
+
+__global__ void __launch_bounds__(256) mr_coop_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ order,
+                                                      const float* __restrict__ mask_logit, int ms,
+                                                      const int32_t* __restrict__ cls_idx, int H, int W, float frac_thr,
+                                                      uint8_t* __restrict__ occ, unsigned int* __restrict__ counters,
+                                                      int32_t* __restrict__ keep_flag, const MrSched* __restrict__ sc) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int steps = sc->steps;
+  for (int t = 0; t < steps; ++t) {
+    int act[8], nact = 0;
+    for (int c = 0; c < 8; ++c)
+      if (sc->count[c] > t) act[nact++] = sc->slot[c][t];
+    const int mine = blockIdx.x % nact, part = blockIdx.x / nact;
+    const int nparts = ((int)gridDim.x - mine + nact - 1) / nact;
+    const int pos = act[mine];
+    const int det = order[pos];
+    const int cls = cls_idx[det] - 1;
+    const BoxI b = int_box(boxes + (int64_t)det * 4, H, W);
+    const int cw = b.x_1 - b.x_0, ch = b.y_1 - b.y_0;
+    const float* ml = mask_logit + (int64_t)det * ms * ms;
+    uint8_t* oc = occ + (int64_t)cls * H * W;
+    const int64_t total = (cw > 0 && ch > 0) ? (int64_t)cw * ch : 0;
+    // ---- count
+    unsigned int msum = 0, osum = 0;
+    for (int64_t i = (int64_t)part * blockDim.x + threadIdx.x; i < total; i += (int64_t)nparts * blockDim.x) {
+      const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
+      const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
+      if (v > 0.f) { msum++; if (__ldcg(oc + (int64_t)y * W + x) >= 1) osum++; }   // L2 reads: other SMs wrote it
+    }
+    for (int o = 16; o > 0; o >>= 1) { msum += __shfl_xor_sync(0xffffffffu, msum, o); osum += __shfl_xor_sync(0xffffffffu, osum, o); }
+    if ((threadIdx.x & 31) == 0 && (msum | osum)) { atomicAdd(counters + 2 * pos, msum); atomicAdd(counters + 2 * pos + 1, osum); }
+    grid.sync();
+    // ---- decide + apply
+    const unsigned int ms_all = __ldcg(counters + 2 * pos), os_all = __ldcg(counters + 2 * pos + 1);
+    const bool keep = ms_all != 0 && !((double)os_all / (double)ms_all > (double)frac_thr);
+    if (part == 0 && threadIdx.x == 0) keep_flag[pos] = keep ? 1 : 0;
+    if (keep) {
+      for (int64_t i = (int64_t)part * blockDim.x + threadIdx.x; i < total; i += (int64_t)nparts * blockDim.x) {
+        const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
+        const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
+        if (v > 0.f) { uint8_t* q = oc + (int64_t)y * W + x; __stcg(q, (uint8_t)(__ldcg(q) + 1)); }
+      }
+    }
+    grid.sync();
   }
 }
 
@@ -217,14 +287,34 @@ extern "C" int vps_mask_removal(const float* boxes, const int32_t* order, int k,
   cudaMemsetAsync(occ, 0, (size_t)num_things * H * W, st);
   cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 2 * k, st);
   cudaMemsetAsync(keep_flag, 0, sizeof(int32_t) * k, st);
-  for (int pos = 0; pos < k; ++pos) {
-    mr_count_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, occ, counters);
-    mr_apply_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, frac_thr, occ,
-                                         counters, keep_flag);
+  static MrSched* d_sched = nullptr;
+  static int coop_ok = -1, coop_grid = 0;
+  if (coop_ok < 0) {
+    int dev = 0, sup = 0, nsm = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sup, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mr_coop_kernel, 256, 0);
+    coop_ok = (sup && per_sm >= 1 && k <= MAX_DET_K && cudaMalloc(&d_sched, sizeof(MrSched)) == cudaSuccess) ? 1 : 0;
+    coop_grid = nsm;
+  }
+  if (coop_ok == 1 && k <= MAX_DET_K && num_things <= 8) {
+    mr_schedule_kernel<<<1, 32, 0, st>>>(order, cls_idx, k, k_dev, num_things, d_sched);
+    void* args[] = {(void*)&boxes, (void*)&order, (void*)&mask_logit, (void*)&msize, (void*)&cls_idx, (void*)&H, (void*)&W,
+                    (void*)&frac_thr, (void*)&occ, (void*)&counters, (void*)&keep_flag, (void*)&d_sched};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)mr_coop_kernel, dim3(coop_grid), dim3(256), args, 0, st);
+    if (e != cudaSuccess) { vps::set_error("mask_removal: cooperative launch: %s", cudaGetErrorString(e)); return VPS_E_CUDA; }
+    vps::count_launch(2);
+  } else {
+    for (int pos = 0; pos < k; ++pos) {
+      mr_count_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, occ, counters);
+      mr_apply_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, frac_thr, occ,
+                                           counters, keep_flag);
+    }
+    vps::count_launch(2 * k);
   }
   mr_compact_kernel<<<1, 32, 0, st>>>(order, keep_flag, k, k_dev, keep_sorted, nkeep);
   VPS_CUDA_LAST("mask_removal");
-  vps::count_launch(2 * k);
   return VPS_OK;
 }
 
