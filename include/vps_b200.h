@@ -90,9 +90,6 @@ int vps_conv2d_tc(const vps_conv_args* a, void* stream);
  * the stride phases of a ConvTranspose2d (submodules.py:33-37, fcn_mask_head.py:66-71) in one persistent launch. */
 int vps_conv2d_tc_multi(const vps_conv_args* a, int nprob, void* stream);
 int vps_conv2d_simt(const vps_conv_args* a, void* stream);
-/* 3x3 / stride 1 / pad 1 convolution with cout == 2 (FlowNet2 predict_flow, submodules.py:30-31): input-streaming
- * CUDA-core kernel, one warp per output pixel; same args as vps_conv2d_simt (w = f32 [3][3][cin][2]). */
-int vps_conv3x3_thin(const vps_conv_args* a, void* stream);
 /* OIHW fp32 (torch layout, on device) -> packed layouts.  scale[cout] (may be NULL) is folded in
  * (frozen BatchNorm: resnet.py:519-526).  transposed != 0: src is IOHW (ConvTranspose2d). */
 int vps_pack_weights_tc(const float* w_oihw, const float* scale, void* dst_bf16, int cout, int cin,

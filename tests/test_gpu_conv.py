@@ -28,9 +28,9 @@ CASES = [
     (1, 128, 128, 24, 24, 5, 2, 2),      # FlowNet 5x5 s2
     (3, 256, 256, 14, 14, 3, 1, 1),      # mask-head shape (batch of RoIs)
     (1, 192, 1024, 1, 300, 1, 1, 0),     # Linear as 1x1 over a row of "pixels"
-    (1, 1026, 2, 8, 16, 3, 1, 1),        # predict_flow5: thin-output streaming kernel, ragged cin
+    (1, 1026, 2, 8, 16, 3, 1, 1),        # predict_flow5: ragged cin, cout 2
     (1, 194, 2, 32, 48, 3, 1, 1),        # predict_flow2
-    (1, 16, 2, 40, 56, 3, 1, 1),         # FlowNetFusion predict_flow0 (2 lanes per pixel)
+    (1, 16, 2, 40, 56, 3, 1, 1),         # FlowNetFusion predict_flow0 (bk=16 path)
     (1, 12, 64, 32, 64, 7, 2, 3),        # FlowNetS conv1 stem (cin 12): bk=16 implicit GEMM without s2d
     (1, 48, 32, 20, 36, 3, 1, 1),        # cin < 64
 ]

@@ -61,7 +61,7 @@ def check(status, what=""):
 # every symbol include/vps_b200.h declares (tests assert the .so exports all of them)
 EXPORTS = [
     "vps_last_error", "vps_version", "vps_launch_count", "vps_add_launch_count",
-    "vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_conv2d_simt", "vps_conv3x3_thin", "vps_pack_weights_tc", "vps_pack_weights_simt",
+    "vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_conv2d_simt", "vps_pack_weights_tc", "vps_pack_weights_simt",
     "vps_packed_tc_bytes", "vps_im2col",
     "vps_correlation", "vps_correlation_tc", "vps_correlation_simt", "vps_resample2d", "vps_channelnorm", "vps_flownet_input", "vps_flow_deconv",
     "vps_nchw_to_nhwc", "vps_nhwc_to_nchw", "vps_copy_scale", "vps_axpby",

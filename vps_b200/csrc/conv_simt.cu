@@ -170,98 +170,3 @@ extern "C" int vps_conv2d_simt(const vps_conv_args* a, void* stream) {
   if (a->x.dtype == VPS_BF16 && a->y.dtype == VPS_F32) return launch_simt<__nv_bfloat16, float>(a, p, grid, st);
   return launch_simt<float, __nv_bfloat16>(a, p, grid, st);
 }
-
-// ---------------------------------------------------------------------------------------------------------------
-// Thin-output 3x3 convolution (cout <= 4): FlowNet2 `predict_flow` (C -> 2, submodules.py:30-31).  These layers are
-// pure input streaming (2*9*C MAC per pixel): one warp per output pixel, lanes split the channels with 16-byte
-// loads, fp32 accumulation, warp-shuffle reduction.  Weights f32 [kh][kw][cin][cout] (the simt packing).
-namespace {
-template <typename TI, typename TO, int V, int CO>
-__global__ void __launch_bounds__(256) conv3x3_thin_kernel(vps::TV<const TI> x, vps::TV<TO> y, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, int act, float slope,
-                                                           float out_scale, int64_t npix, int G) {
-  // G (power of two <= 32) lanes cooperate on one output pixel, 32/G pixels per warp
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % G, slot = lane / G, ppw = 32 / G;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int C = x.c;
-  for (int64_t base = warp * ppw; base < npix; base += nwarps * ppw) {
-    const int64_t pix = base + slot;
-    const bool pv = pix < npix;
-    const int ox = pv ? (int)(pix % y.w) : 0;
-    const int64_t t = pv ? pix / y.w : 0;
-    const int oy = (int)(t % y.h), n = (int)(t / y.h);
-    float acc[CO];
-#pragma unroll
-    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
-    if (pv) {
-      for (int r = 0; r < 3; ++r) {
-        const int iy = oy - 1 + r;
-        if (iy < 0 || iy >= x.h) continue;
-        for (int s = 0; s < 3; ++s) {
-          const int ix = ox - 1 + s;
-          if (ix < 0 || ix >= x.w) continue;
-          const TI* xp = x.p + x.off(n, iy, ix);
-          const float* wp = w + (int64_t)(r * 3 + s) * C * CO;
-          for (int c = sub * V; c < C; c += G * V) {
-            float v[V];
-            if (V > 1 && c + V <= C) {
-              vps::ldv<TI, V>(xp + c, v);
-            } else {
-#pragma unroll
-              for (int j = 0; j < V; ++j) v[j] = (c + j < C) ? vps::ldf<TI>(xp + c + j) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              if (c + j < C) {
-#pragma unroll
-                for (int o = 0; o < CO; ++o) acc[o] = fmaf(v[j], __ldg(wp + (int64_t)(c + j) * CO + o), acc[o]);
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < CO; ++o)
-      for (int sft = G >> 1; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
-    if (pv && sub == 0) {
-      TO* yp = y.p + y.off(n, oy, ox);
-#pragma unroll
-      for (int o = 0; o < CO; ++o) {
-        float v = acc[o] + (bias ? bias[o] : 0.f);
-        vps::stf<TO>(yp + o, vps::apply_act(v, act, slope) * out_scale);
-      }
-    }
-  }
-}
-}  // namespace
-
-extern "C" int vps_conv3x3_thin(const vps_conv_args* a, void* stream) {
-  VPS_CHECK_ARG(a->kh == 3 && a->kw == 3 && a->sh == 1 && a->sw == 1 && a->ph == 1 && a->pw == 1, "conv3x3_thin: 3x3 s1 p1 only");
-  VPS_CHECK_ARG(a->cout == 2 && a->cin == a->x.c && a->res.ptr == nullptr, "conv3x3_thin: cout must be 2, no residual");
-  VPS_CHECK_ARG(a->oy_mul == 1 && a->ox_mul == 1 && a->oy_off == 0 && a->ox_off == 0 && a->oh == a->x.h && a->ow == a->x.w &&
-                    a->y.h == a->x.h && a->y.w == a->x.w, "conv3x3_thin: identity output mapping only");
-  const int64_t npix = (int64_t)a->x.n * a->oh * a->ow;
-  if (!npix) return VPS_OK;
-  const int Vw = a->x.dtype == VPS_F32 ? 4 : 8;
-  const bool vec = a->x.cs % Vw == 0 && ((uintptr_t)a->x.ptr & 15) == 0;
-  int G = 1;
-  while (G < 32 && G * (vec ? Vw : 1) < a->x.c) G <<= 1;       // lanes per pixel
-  int64_t blocks = (npix * G + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  cudaStream_t st = (cudaStream_t)stream;
-  const float* w = (const float*)a->w;
-#define THIN(TI, TO, V) conv3x3_thin_kernel<TI, TO, V, 2><<<(int)blocks, 256, 0, st>>>(vps::tv<const TI>(a->x), vps::tv<TO>(a->y), w, a->bias, a->act, a->slope, a->out_scale, npix, G)
-  if (a->x.dtype == VPS_F32) {
-    if (a->y.dtype == VPS_F32) { if (vec) THIN(float, float, 4); else THIN(float, float, 1); }
-    else { if (vec) THIN(float, __nv_bfloat16, 4); else THIN(float, __nv_bfloat16, 1); }
-  } else {
-    if (a->y.dtype == VPS_F32) { if (vec) THIN(__nv_bfloat16, float, 8); else THIN(__nv_bfloat16, float, 1); }
-    else { if (vec) THIN(__nv_bfloat16, __nv_bfloat16, 8); else THIN(__nv_bfloat16, __nv_bfloat16, 1); }
-  }
-#undef THIN
-  VPS_CUDA_LAST("conv3x3_thin");
-  return VPS_OK;
-}

@@ -41,8 +41,15 @@ struct ConvTcParams {
   int n_tiles_n, block_n;
   int kh, kw, sh, sw, ph, pw;
   int cin_chunks;
-  int num_stages;
+  int a_stages, b_stages;     // operand rings (A: activation boxes, B: weight boxes)
+  int halo;                   // 1: one (th+kh-1) x (tw+kw-1) activation box per channel chunk feeds all kh*kw taps
+  int halo_w;                 // tw + kw - 1 (pixels per halo row)
+  int a_stage_bytes;          // bytes of one A ring slot (multiple of 1024)
+  int a_box_bytes;            // bytes one A TMA box delivers
+  int rowg;                   // halo mode: 1 = one B ring slot holds the kw taps of a filter row (one barrier round per row)
+  int nk_last;                // K16 slabs of the last channel chunk that hold real channels (the rest is zero padding)
   int total_tiles;
+  long long* stats;           // optional [grid][8] clock counters (VPS_CONV_STATS=1), else NULL
   void* y;
   int y_h, y_w, y_cs, y_dtype, y_vec;
   int oy_mul, oy_off, ox_mul, ox_off;
@@ -97,6 +104,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
@@ -109,6 +123,18 @@ __device__ __forceinline__ void tc_fence_before() {
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// true in exactly one lane of the (converged) warp -- the same lane every time for a full mask
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -127,10 +153,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 // K-major operand tile whose rows are bk*2 bytes: bk=64 -> 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart;
 // bk=16 -> 32-byte rows, SWIZZLE_32B, 8-row groups 256 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int bk) {
+// sbo = byte distance between consecutive 8-row groups (8 * row bytes for a dense tile; the halo row pitch when the
+// 8 rows of a group are 8 consecutive pixels of one halo row).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int bk, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
-  d |= (uint64_t)((bk == 64 ? 1024 : 256) >> 4) << 32;         // stride byte offset, bits [32,46)
+  d |= (uint64_t)(sbo >> 4) << 32;                             // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                                      // descriptor version (sm_100)
   d |= (uint64_t)(bk == 64 ? 2 : 6) << 61;                     // layout type SWIZZLE_128B / SWIZZLE_32B
   return d;
@@ -177,9 +205,18 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     } else {
+      const int ng = nv >> 2;                      // float4 groups (n0 % 32 == 0 keeps them 16-byte aligned)
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < ng) {
+          const float4 b = __ldg(bp + j);
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < nv) v[j] += __ldg(p.bias + n0 + j);
+        if (j >= 4 * ng && j < nv) v[j] += __ldg(p.bias + n0 + j);
     }
   }
   const bool has_res = p.res != nullptr;
@@ -211,9 +248,22 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
           }
         }
       } else {
+        const int ng = p.res_vec ? (nv >> 3) : 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < ng) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(rp + 8 * g);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(b2[t]);
+              v[8 * g + 2 * t] += f.x; v[8 * g + 2 * t + 1] += f.y;
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < nv) v[j] += __bfloat162float(rp[j]);
+          if (j >= 8 * ng && j < nv) v[j] += __bfloat162float(rp[j]);
       }
     } else {
       const float* rp = (const float*)p.res + ro;
@@ -258,9 +308,23 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
         *(uint4*)(yp + j) = pk;
       }
     } else {
+      const int ng = p.y_vec ? (nv >> 3) : 0;      // 16-byte groups of a partial chunk, then a scalar tail
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g < ng) {
+          const int j = 8 * g;
+          uint4 pk;
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+          pk.x = *(uint32_t*)&b0; pk.y = *(uint32_t*)&b1; pk.z = *(uint32_t*)&b2; pk.w = *(uint32_t*)&b3;
+          *(uint4*)(yp + j) = pk;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < nv) yp[j] = __float2bfloat16_rn(v[j]);
+        if (j >= 8 * ng && j < nv) yp[j] = __float2bfloat16_rn(v[j]);
     }
   } else {
     float* yp = (float*)p.y + yo;
@@ -276,9 +340,13 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *(float4*)(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
+      const int ng = p.y_vec ? (nv >> 2) : 0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g < ng) *(float4*)(yp + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < nv) yp[j] = v[j];
+        if (j >= 4 * ng && j < nv) yp[j] = v[j];
     }
   }
 }
@@ -296,6 +364,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   int acc = 0;
   uint32_t acc_phase = 0;
+  long long st_w = 0, st_e = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const int prob = tile / p.tiles_per_prob;
     const int t_in = tile - prob * p.tiles_per_prob;
@@ -310,7 +379,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
     const int nbase = n_idx * p.block_n;
     const int nlim = min(p.cout, nbase + p.block_n);
 
+    const long long t0 = p.stats ? clock64() : 0;
     mbar_wait(tfull0 + 8u * acc, acc_phase);
+    const long long t1 = p.stats ? clock64() : 0;
+    st_w += t1 - t0;
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
     uint32_t ra[32], rb[32];
@@ -331,8 +403,189 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
     tmem_ld_wait();
     tc_fence_before();
     mbar_arrive(tempty0 + 8u * acc);
+    if (p.stats) st_e += clock64() - t1;
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
+  }
+  if (p.stats && warp == 2 && lane == 0) { p.stats[blockIdx.x * 8 + 6] = st_w; p.stats[blockIdx.x * 8 + 7] = st_e; }
+}
+
+
+// ---------------------------------------------------------------- single-issuer roles (warps 0 and 1)
+// Both run their loops warp-uniformly and pick the issuing lane with elect.sync: code under `if (lane == 0)` is
+// divergent to the compiler, which then wraps every TMA / tcgen05 instruction in a uniformity loop.  A lone warp
+// retires a dependent instruction every ~5 clk, so the per-step instruction count of these loops IS the pipeline
+// rate for small N (measured: 110 SASS instructions = 500 clk per K step): the loops are specialised on the mode
+// and, in halo mode, one barrier round covers a whole filter row (kw taps, 4*kw MMAs).
+struct Ring {
+  uint32_t a_base, a_stage_bytes, b_base, b_stage_bytes, bar_base;
+  __device__ __forceinline__ uint32_t afull(int s) const { return bar_base + 8u * s; }
+  __device__ __forceinline__ uint32_t aempty(int s) const { return bar_base + 8u * (MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t bfull(int s) const { return bar_base + 8u * (2 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t bempty(int s) const { return bar_base + 8u * (3 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t tfull(int a) const { return bar_base + 8u * (4 * MAX_STAGES + a); }
+  __device__ __forceinline__ uint32_t tempty(int a) const { return bar_base + 8u * (4 * MAX_STAGES + 2 + a); }
+};
+
+template <bool HALO, bool ROWG, bool STATS>
+__device__ __forceinline__ void producer_loop(const ConvTcParams& p, const Ring& rg, const CUtensorMap* tmA,
+                                              const CUtensorMap* tmB0, const CUtensorMap* tmB1, const CUtensorMap* tmB2,
+                                              const CUtensorMap* tmB3, int lane) {
+  const int bk = p.bk, kw = p.kw, cin_chunks = p.cin_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
+  const int ngrp = ROWG ? p.kh : p.kh * p.kw;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes;
+  int as = 0, bs = 0;
+  uint32_t aphase = 0, bphase = 0;
+  long long st_a = 0, st_b = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int prob = tile / p.tiles_per_prob;
+    const int t_in = tile - prob * p.tiles_per_prob;
+    const int n_idx = t_in % p.n_tiles_n;
+    const int m_idx = t_in / p.n_tiles_n;
+    const int img = m_idx / tiles_per_img;
+    const int rem = m_idx - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int x_base = tx * p.tw * p.sw - p.pw_[prob];
+    const int y_base = ty * p.th * p.sh - p.ph_[prob];
+    const int n0 = n_idx * p.block_n;
+    const CUtensorMap* tmB = prob == 0 ? tmB0 : (prob == 1 ? tmB1 : (prob == 2 ? tmB2 : tmB3));
+    for (int cc = 0; cc < cin_chunks; ++cc) {
+      if (HALO) {
+        const long long t0 = STATS ? clock64() : 0;
+        mbar_wait(rg.aempty(as), aphase ^ 1);
+        if (STATS) st_a += clock64() - t0;
+        if (elect_one()) {
+          mbar_expect_tx(rg.afull(as), a_box_bytes);
+          tma_load_4d(rg.a_base + as * rg.a_stage_bytes, tmA, rg.afull(as), cc * bk, x_base, y_base, img);
+        }
+        if (++as == a_stages) { as = 0; aphase ^= 1; }
+      }
+      int r = 0, sx = 0;
+      for (int g = 0; g < ngrp; ++g) {
+        if (!HALO) {
+          const long long t0 = STATS ? clock64() : 0;
+          mbar_wait(rg.aempty(as), aphase ^ 1);
+          if (STATS) st_a += clock64() - t0;
+          if (elect_one()) {
+            mbar_expect_tx(rg.afull(as), a_box_bytes);
+            tma_load_4d(rg.a_base + as * rg.a_stage_bytes, tmA, rg.afull(as), cc * bk, x_base + sx, y_base + r, img);
+          }
+          if (++as == a_stages) { as = 0; aphase ^= 1; }
+          if (++sx == kw) { sx = 0; ++r; }
+        }
+        const long long t1 = STATS ? clock64() : 0;
+        mbar_wait(rg.bempty(bs), bphase ^ 1);
+        if (STATS) st_b += clock64() - t1;
+        if (elect_one()) {
+          mbar_expect_tx(rg.bfull(bs), rg.b_stage_bytes);
+          tma_load_3d(rg.b_base + bs * rg.b_stage_bytes, tmB, rg.bfull(bs), cc * bk, n0, ROWG ? g * kw : g);
+        }
+        if (++bs == b_stages) { bs = 0; bphase ^= 1; }
+      }
+    }
+  }
+  if (STATS && lane == 0) { p.stats[blockIdx.x * 8 + 0] = st_a; p.stats[blockIdx.x * 8 + 1] = st_b; }
+}
+
+// the (up to) four K16 MMAs of one tap: 64 channels = one SWIZZLE_128B row; +2 in the (addr >> 4) field = 32 bytes
+template <bool BK64>
+__device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint64_t a_hi, uint64_t b_hi, uint32_t a_addr, uint32_t b_addr,
+                                          uint32_t idesc, int nk, uint32_t accumulate) {
+  const uint64_t adesc = a_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+  const uint64_t bdesc = b_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+  umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+  if (BK64) {
+    if (nk > 1) umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+    if (nk > 2) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+    if (nk > 3) umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+  }
+}
+
+template <bool HALO, bool ROWG, bool BK64, bool STATS>
+__device__ __forceinline__ void mma_loop(const ConvTcParams& p, const Ring& rg, uint32_t tmem_base, int lane) {
+  constexpr uint32_t row_bytes = BK64 ? 128u : 32u;
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                         ((uint32_t)(BLOCK_M >> 4) << 24);
+  const int kw = p.kw, cin_chunks = p.cin_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
+  const int ngrp = ROWG ? p.kh : p.kh * p.kw;
+  const int nk_last = p.nk_last;
+  const uint32_t halo_pitch = (uint32_t)p.halo_w * row_bytes;
+  const uint32_t tap_b_bytes = (uint32_t)p.block_n * row_bytes;
+  // descriptor high words are loop constants; the low word is (smem address >> 4)
+  const uint64_t a_hi = make_smem_desc(0, BK64 ? 64 : 16, HALO ? halo_pitch : 8u * row_bytes);
+  const uint64_t b_hi = make_smem_desc(0, BK64 ? 64 : 16, 8u * row_bytes);
+  int as = 0, bs = 0, acc = 0;
+  uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+  long long st_a = 0, st_b = 0, st_t = 0;
+  const long long t_begin = STATS ? clock64() : 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const long long t2 = STATS ? clock64() : 0;
+    mbar_wait(rg.tempty(acc), acc_phase ^ 1);
+    if (STATS) st_t += clock64() - t2;
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+    uint32_t first = 0;
+    for (int cc = 0; cc < cin_chunks; ++cc) {
+      const int nk = cc == cin_chunks - 1 ? nk_last : 4;
+      uint32_t a_row = 0, a_tap = 0;
+      int a_cur = 0, sx = 0;
+      if (HALO) {
+        const long long t0 = STATS ? clock64() : 0;
+        mbar_wait(rg.afull(as), aphase);
+        if (STATS) st_a += clock64() - t0;
+        a_row = a_tap = rg.a_base + as * rg.a_stage_bytes;
+        a_cur = as;
+        if (++as == a_stages) { as = 0; aphase ^= 1; }
+      }
+      for (int g = 0; g < ngrp; ++g) {
+        if (!HALO) {
+          const long long t0 = STATS ? clock64() : 0;
+          mbar_wait(rg.afull(as), aphase);
+          if (STATS) st_a += clock64() - t0;
+          a_tap = rg.a_base + as * rg.a_stage_bytes;
+          a_cur = as;
+          if (++as == a_stages) { as = 0; aphase ^= 1; }
+        }
+        const long long t1 = STATS ? clock64() : 0;
+        mbar_wait(rg.bfull(bs), bphase);
+        if (STATS) st_b += clock64() - t1;
+        tc_fence_after();
+        const uint32_t b_addr = rg.b_base + bs * rg.b_stage_bytes;
+        if (elect_one()) {
+          if (ROWG) {      // the kw taps of filter row g: A start moves one pixel (row_bytes) per tap
+            uint32_t at = a_row, bt = b_addr;
+            issue_tap<BK64>(d_tmem, a_hi, b_hi, at, bt, idesc, nk, first);
+            for (int j = 1; j < kw; ++j) {
+              at += row_bytes; bt += tap_b_bytes;
+              issue_tap<BK64>(d_tmem, a_hi, b_hi, at, bt, idesc, nk, 1u);
+            }
+          } else {
+            issue_tap<BK64>(d_tmem, a_hi, b_hi, a_tap, b_addr, idesc, nk, first);
+          }
+          umma_commit(rg.bempty(bs));
+          if (!HALO || g == ngrp - 1) umma_commit(rg.aempty(a_cur));
+        }
+        first = 1;
+        if (++bs == b_stages) { bs = 0; bphase ^= 1; }
+        if (HALO) {
+          if (ROWG) {
+            a_row += halo_pitch;
+          } else {          // next tap: one pixel to the right, or the start of the next halo row
+            a_tap += row_bytes;
+            if (++sx == kw) { sx = 0; a_row += halo_pitch; a_tap = a_row; }
+          }
+        }
+      }
+    }
+    if (elect_one()) umma_commit(rg.tfull(acc));
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (STATS && lane == 0) {
+    p.stats[blockIdx.x * 8 + 2] = st_a; p.stats[blockIdx.x * 8 + 3] = st_b; p.stats[blockIdx.x * 8 + 4] = st_t;
+    p.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;
   }
 }
 
@@ -345,23 +598,28 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   // 1024-byte aligned operand ring (SWIZZLE_128B requirement)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t row_bytes = (uint32_t)p.bk * 2u;
-  const uint32_t a_stage_bytes = BLOCK_M * row_bytes;
-  const uint32_t stage_bytes = a_stage_bytes + (uint32_t)p.block_n * row_bytes;
-  const uint32_t bar_base = smem_base + (uint32_t)p.num_stages * stage_bytes;
-  // barrier slots (8 B each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], tmem ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t a_stage_bytes = (uint32_t)p.a_stage_bytes;
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * row_bytes * (p.rowg ? (uint32_t)p.kw : 1u);
+  const uint32_t b_base = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
+  // barrier slots (8 B each): afull, aempty, bfull, bempty [MAX_STAGES each], tmem_full[2], tmem_empty[2], tmem ptr
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (4 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (4 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -383,74 +641,30 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int num_k = p.kh * p.kw * p.cin_chunks;
-  const int tiles_per_img = p.tiles_y * p.tiles_x;
-
+  Ring rg;
+  rg.a_base = smem_base; rg.a_stage_bytes = a_stage_bytes; rg.b_base = b_base; rg.b_stage_bytes = b_stage_bytes;
+  rg.bar_base = bar_base;
+  const bool st = p.stats != nullptr;
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int prob = tile / p.tiles_per_prob;
-        const int t_in = tile - prob * p.tiles_per_prob;
-        const int n_idx = t_in % p.n_tiles_n;
-        const int m_idx = t_in / p.n_tiles_n;
-        const int img = m_idx / tiles_per_img;
-        const int rem = m_idx - img * tiles_per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int x_base = tx * p.tw * p.sw - p.pw_[prob];
-        const int y_base = ty * p.th * p.sh - p.ph_[prob];
-        const CUtensorMap* tmB = prob == 0 ? &tmB0 : (prob == 1 ? &tmB1 : (prob == 2 ? &tmB2 : &tmB3));
-        for (int r = 0; r < p.kh; ++r) {
-          for (int s = 0; s < p.kw; ++s) {
-            for (int cc = 0; cc < p.cin_chunks; ++cc) {
-              mbar_wait(empty_bar(stage), phase ^ 1);
-              const uint32_t a_dst = smem_base + stage * stage_bytes;
-              const uint32_t b_dst = a_dst + a_stage_bytes;
-              mbar_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_4d(a_dst, &tmA, full_bar(stage), cc * p.bk, x_base + s, y_base + r, img);
-              tma_load_2d(b_dst, tmB, full_bar(stage), ((r * p.kw + s) * p.cin_chunks + cc) * p.bk, n_idx * p.block_n);
-              if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-            }
-          }
-        }
-      }
-    }
+#define VPS_PROD(H, R) \
+    do { if (st) producer_loop<H, R, true>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); \
+         else producer_loop<H, R, false>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); } while (0)
+    if (p.halo) { if (p.rowg) VPS_PROD(true, true); else VPS_PROD(true, false); }
+    else VPS_PROD(false, false);
+#undef VPS_PROD
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-                             ((uint32_t)(BLOCK_M >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int kc = 0; kc < num_k; ++kc) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(a_addr, p.bk);
-          const uint64_t bdesc = make_smem_desc(a_addr + a_stage_bytes, p.bk);
-          const int nk = p.bk >> 4;
-          for (int k = 0; k < nk; ++k) {
-            // advance 16 bf16 = 32 B inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      (uint32_t)((kc | k) != 0));
-          }
-          umma_commit(empty_bar(stage));
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
+#define VPS_MMA(H, R, B) \
+    do { if (st) mma_loop<H, R, B, true>(p, rg, tmem_base, lane); else mma_loop<H, R, B, false>(p, rg, tmem_base, lane); } while (0)
+    if (p.bk == 64) {
+      if (p.halo) { if (p.rowg) VPS_MMA(true, true, true); else VPS_MMA(true, false, true); }
+      else VPS_MMA(false, false, true);
+    } else {
+      if (p.halo) { if (p.rowg) VPS_MMA(true, true, false); else VPS_MMA(true, false, false); }
+      else VPS_MMA(false, false, false);
     }
+#undef VPS_MMA
   } else {
     // ===================== epilogue (warps 2..9) =====================
     switch (p.act) {
@@ -564,16 +778,34 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
   const int cin_pad = cin_pad_for(a->cin, bk);
   const int cout_pad = (a->cout + 15) / 16 * 16;
   p.n_img = a->x.n; p.oh = a->oh; p.ow = a->ow;
-  // pixel patch: minimise padded area; th*tw == 128, box extent tw*sw <= 256
-  int best_tw = 16; int64_t best_area = -1;
-  const int cands[5] = {16, 8, 32, 64, 128};
-  for (int i = 0; i < 5; ++i) {
-    const int tw = cands[i], th = 128 / tw;
-    if (tw * a->sw > 256 || th * a->sh > 256) continue;
-    const int64_t area = (int64_t)vps::cdiv(a->ow, tw) * tw * vps::cdiv(a->oh, th) * th;
-    if (best_area < 0 || area < best_area) { best_area = area; best_tw = tw; }
+  // halo mode (stride 1, more than one tap): the 8 rows of an MMA row group are 8 consecutive pixels of one halo row,
+  // so the tile is 16 x 8 pixels and every tap reads the same (16+kh-1) x (8+kw-1) box at a shifted start address.
+  static int halo_env = -1;
+  if (halo_env < 0) {
+    const char* e = getenv("VPS_CONV_HALO");
+    halo_env = e ? atoi(e) : 2;                         // 0 = off, 1 = on wherever legal, 2 = heuristic
   }
-  p.tw = best_tw; p.th = 128 / best_tw;
+  const bool halo_ok = a->sh == 1 && a->sw == 1 && a->kh * a->kw > 1 && a->kh <= 8 && a->kw <= 8;
+  const bool halo = halo_ok && halo_env != 0;
+  p.halo = halo ? 1 : 0;
+  if (halo) {
+    p.tw = 8; p.th = 16;
+  } else {
+    // pixel patch: minimise padded area; th*tw == 128, box extent tw*sw <= 256
+    int best_tw = 16; int64_t best_area = -1;
+    const int cands[5] = {16, 8, 32, 64, 128};
+    for (int i = 0; i < 5; ++i) {
+      const int tw = cands[i], th = 128 / tw;
+      if (tw * a->sw > 256 || th * a->sh > 256) continue;
+      const int64_t area = (int64_t)vps::cdiv(a->ow, tw) * tw * vps::cdiv(a->oh, th) * th;
+      if (best_area < 0 || area < best_area) { best_area = area; best_tw = tw; }
+    }
+    p.tw = best_tw; p.th = 128 / best_tw;
+  }
+  p.halo_w = p.tw + a->kw - 1;
+  const int halo_h = p.th + a->kh - 1;
+  p.a_box_bytes = halo ? halo_h * p.halo_w * bk * 2 : BLOCK_M * bk * 2;
+  p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
   p.tiles_x = vps::cdiv(a->ow, p.tw); p.tiles_y = vps::cdiv(a->oh, p.th);
   // N tile: pick the divisor of cout_pad (multiple of 16, <= 256) that minimises a simple time model
   //   waves(bn) * k_steps * max(fixed per-step latency, MMA time 2*bn clk, stage bytes / per-SM L2 bandwidth)
@@ -586,19 +818,35 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
       if (cout_pad % bn) continue;
       const int64_t tiles = m_tiles * (cout_pad / bn);
       const double waves = (double)((tiles + g_num_sms - 1) / g_num_sms);
-      const double step = fmax(fmax(350.0, 2.0 * bn), (double)((BLOCK_M + bn) * bk * 2) / 80.0);
       const double epi = 40.0 * bn;     // epilogue clocks per tile (not hidden when a CTA runs a single tile)
-      const double t = waves * ((double)(a->kh * a->kw * (cin_pad / bk)) * step + epi);
+      double t;
+      if (halo) {   // per tap: MMA time / operand reads from smem / weight box; per chunk: one halo box
+        const double step = fmax(fmax(215.0, 2.0 * bn), (double)(bn * bk * 2) / 40.0);
+        t = waves * ((double)(cin_pad / bk) * ((double)(a->kh * a->kw) * step + (double)p.a_box_bytes / 20.0) + epi);
+      } else {
+        const double step = fmax(fmax(350.0, 2.0 * bn), (double)((BLOCK_M + bn) * bk * 2) / 80.0);
+        t = waves * ((double)(a->kh * a->kw * (cin_pad / bk)) * step + epi);
+      }
       if (best < 0 || t < best * 0.999) { best = t; block_n = bn; }
     }
   }
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
   p.kh = a->kh; p.kw = a->kw; p.sh = a->sh; p.sw = a->sw;
   p.cin_chunks = cin_pad / bk;
-  const int stage_bytes = (BLOCK_M + block_n) * bk * 2;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  p.num_stages = stages;
+  // halo mode: one B ring slot = the kw taps of a filter row when that fits (<= 48 KB) -- one barrier round per row
+  p.rowg = (halo && a->kw > 1 && a->kw * block_n * bk * 2 <= 48 * 1024) ? 1 : 0;
+  p.nk_last = bk == 64 ? (a->cin - (p.cin_chunks - 1) * 64 + 15) / 16 : 1;
+  const int b_stage_bytes = block_n * bk * 2 * (p.rowg ? a->kw : 1);
+  if (halo) {
+    p.a_stages = p.cin_chunks >= 3 ? 3 : 2;
+    int bst = (200 * 1024 - p.a_stages * p.a_stage_bytes) / b_stage_bytes;
+    p.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
+    VPS_CHECK_ARG(p.b_stages >= 2, "conv2d_tc: halo ring does not fit");
+  } else {
+    int stages = (200 * 1024) / (p.a_stage_bytes + b_stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.a_stages = p.b_stages = stages;
+  }
   p.nprob = nprob;
   p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
   p.total_tiles = p.tiles_per_prob * nprob;
@@ -627,7 +875,8 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
     cuuint64_t dims[4] = {(cuuint64_t)a->x.c, (cuuint64_t)a->x.w, (cuuint64_t)a->x.h, (cuuint64_t)a->x.n};
     cuuint64_t strides[3] = {(cuuint64_t)a->x.cs * 2, (cuuint64_t)a->x.w * a->x.cs * 2,
                              (cuuint64_t)a->x.h * a->x.w * a->x.cs * 2};
-    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.tw * a->sw), (cuuint32_t)(p.th * a->sh), 1};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(halo ? p.halo_w : p.tw * a->sw),
+                         (cuuint32_t)(halo ? halo_h : p.th * a->sh), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)a->sw, (cuuint32_t)a->sh, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x.ptr, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -640,17 +889,19 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
   }
   for (int i = 0; i < MAX_PROB; ++i) {
     const vps_conv_args* q = &args[i < nprob ? i : 0];
+    // packed weights [cout_pad][tap][cin_pad] viewed as {cin_pad, cout_pad, taps}: a box is {bk, block_n, taps-per-slot},
+    // i.e. consecutive K-major [block_n][bk] tiles, one per tap
     const cuuint64_t K = (cuuint64_t)a->kh * a->kw * cin_pad;
-    cuuint64_t dims[2] = {K, (cuuint64_t)cout_pad};
-    cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)q->w, dims, strides, box, estr,
+    cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)(a->kh * a->kw)};
+    cuuint64_t strides[2] = {K * 2, (cuuint64_t)cin_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)block_n, (cuuint32_t)(p.rowg ? a->kw : 1)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)q->w, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
-  const int smem = stages * stage_bytes + 1024 + 8 * (2 * MAX_STAGES + 8);
+  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_stage_bytes + 1024 + 8 * (4 * MAX_STAGES + 8);
   static bool smem_set = false;
   if (!smem_set) {
     if (cudaFuncSetAttribute(conv_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -661,8 +912,29 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
     smem_set = true;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  static int stats_env = -1;
+  static long long* stats_buf = nullptr;
+  if (stats_env < 0) { const char* e = getenv("VPS_CONV_STATS"); stats_env = e ? atoi(e) : 0; }
+  p.stats = nullptr;
+  if (stats_env) {   // debugging aid: per-role barrier-wait clocks, printed after a device sync (never on in production)
+    if (!stats_buf) cudaMalloc(&stats_buf, sizeof(long long) * 8 * 1024);
+    cudaMemsetAsync(stats_buf, 0, sizeof(long long) * 8 * grid, (cudaStream_t)stream);
+    p.stats = stats_buf;
+  }
   conv_igemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], p);
   VPS_CUDA_LAST("conv_igemm_tc_kernel");
+  if (stats_env) {
+    static long long h[8 * 1024];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, stats_buf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    double m[8] = {0};
+    for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / grid;
+    const int tiles_cta = (p.total_tiles + grid - 1) / grid;
+    fprintf(stderr, "conv_tc stats %dx%d %d->%d @%dx%d halo=%d/%d bn=%d bk=%d stages a%d b%d tiles/cta %d steps/tile %d | clk/CTA: total %.0f  "
+            "prod wait Aempty %.0f Bempty %.0f | mma wait Afull %.0f Bfull %.0f tmem-empty %.0f | epi wait tfull %.0f work %.0f\n",
+            a->kh, a->kw, a->cin, a->cout, a->oh, a->ow, p.halo, p.rowg, block_n, bk, p.a_stages, p.b_stages, tiles_cta,
+            a->kh * a->kw * p.cin_chunks, m[5], m[0], m[1], m[2], m[3], m[4], m[6], m[7]);
+  }
   return VPS_OK;
 }
 

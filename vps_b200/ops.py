@@ -149,12 +149,7 @@ def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_aft
     if PROFILE is not None:
         _NOTE["flops"] = 2 * x.shape[0] * a.oh * a.ow * pw.cout * pw.cin * a.kh * a.kw
         _NOTE["tag"] = "%dx%d s%d %d->%d @%dx%d" % (a.kh, a.kw, a.sh, pw.cin, pw.cout, a.oh, a.ow)
-    thin = (pw.cout == 2 and a.kh == 3 and a.kw == 3 and a.sh == 1 and a.sw == 1 and a.ph == 1 and a.pw == 1 and res is None
-            and tuple(omap) == (1, 0, 1, 0) and a.oh == x.shape[1] and a.ow == x.shape[2] and x.dtype == torch.bfloat16)
-    if thin:          # predict_flow: streaming CUDA-core kernel beats a 16-wide tensor-core tile
-        a.w = pw.simt().data_ptr()
-        check(lib().vps_conv3x3_thin(C.byref(a), stream()), "conv3x3_thin")
-    elif use_tc:
+    if use_tc:
         a.cin_gran = pw.gran()
         a.w = pw.tc().data_ptr()
         check(lib().vps_conv2d_tc(C.byref(a), stream()), "conv2d_tc")
