@@ -207,6 +207,11 @@ int vps_rpn_decode(const float* scores_sorted, const int32_t* idx_sorted, int k,
  * ws >= n * ceil(n/64) * 8 bytes. */
 int vps_nms(const float* dets, int n, const int* n_dev, float thr, int32_t* keep_idx, int* nkeep,
             void* ws, int64_t ws_bytes, void* stream);
+/* nb (<= 8) independent NMS problems in one launch pair -- the per-level NMS of get_bboxes_single
+ * (rpn_head.py:55-104): problem b = rows [b*seg, b*seg + ns[b]) of dets (ns = host array; n_dev, if given, is a device
+ * array of nb valid counts), keep_idx + b*seg / nkeep[b] its result.  ws >= nb * seg * ceil(max ns / 64) * 8 bytes. */
+int vps_nms_batch(const float* dets, int nb, int seg, const int* ns, const int* n_dev, float thr,
+                  int32_t* keep_idx, int* nkeep, void* ws, int64_t ws_bytes, void* stream);
 /* dst[i,:] = src[idx[i],:] for i < n (valid count from n_dev if given; rows beyond are zeroed) */
 int vps_gather_rows(const float* src, const int32_t* idx, int n, const int* n_dev, int width, float* dst,
                     void* stream);

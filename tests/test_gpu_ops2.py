@@ -206,6 +206,37 @@ def test_nms_empty_and_device_count(cuda):
     assert keep[:int(nk.item())].tolist() == [0, 2]
 
 
+def test_nms_batch_vs_oracle(cuda):
+    """vps_nms_batch: several independent problems (RPN levels) of different sizes in one launch pair, each equal to
+    the oracle's greedy NMS (nms_kernel.cu:13-131) on the same boxes."""
+    from oracle import ops as O
+    from vps_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    seg, ns = 1000, [1000, 777, 64, 1, 0]
+    dets = torch.zeros(len(ns) * seg, 5)
+    refs = []
+    for b, n in enumerate(ns):
+        if n == 0:
+            refs.append([])
+            continue
+        xy = torch.rand(n, 2, generator=g) * 300
+        wh = torch.rand(n, 2, generator=g) * 80 + 4
+        sc = torch.sort(torch.rand(n, generator=g), descending=True).values
+        d = torch.cat([xy, xy + wh, sc[:, None]], 1)
+        dets[b * seg:b * seg + n] = d
+        _, keep = O.nms(d, 0.7)
+        refs.append(keep.tolist())
+    dd = dets.cuda()
+    keep = torch.full((len(ns) * seg,), -1, dtype=torch.int32, device="cuda")
+    nk = torch.full((len(ns),), -5, dtype=torch.int32, device="cuda")
+    ws = torch.empty(len(ns) * ops.nms_ws_bytes(seg), dtype=torch.uint8, device="cuda")
+    ops.nms_batch(dd, ns, seg, 0.7, keep, nk, ws)
+    torch.cuda.synchronize()
+    for b, n in enumerate(ns):
+        k = int(nk[b].item())
+        assert keep[b * seg:b * seg + k].tolist() == refs[b], "problem %d" % b
+
+
 def test_rpn_level_pipeline(cuda):
     """sigmoid -> stable top-k -> decode -> NMS of one RPN level vs RPNHead.get_bboxes' per-level body."""
     from oracle import ops as O

@@ -130,9 +130,20 @@ __device__ __forceinline__ float dev_iou(const float* a, const float* b) {
   return inter / (sa + sb - inter);
 }
 
-__global__ void nms_mask_kernel(int n_cap, const int* __restrict__ n_dev, float thr, const float* __restrict__ boxes,
-                                unsigned long long* __restrict__ mask, int col_blocks) {
-  const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
+// nb independent problems per launch (the RPN levels): problem b = rows [b*seg, b*seg + n_b) of dets
+struct NmsBatch {
+  int n[8];
+};
+__device__ __forceinline__ int nms_count(const NmsBatch& nb, const int* __restrict__ n_dev, int b) {
+  return n_dev ? min(n_dev[b], nb.n[b]) : nb.n[b];
+}
+
+__global__ void nms_mask_kernel(NmsBatch nb, int seg, const int* __restrict__ n_dev, float thr, const float* __restrict__ boxes_all,
+                                unsigned long long* __restrict__ mask_all, int col_blocks) {
+  const int b = blockIdx.z;
+  const int n = nms_count(nb, n_dev, b);
+  const float* boxes = boxes_all + (int64_t)b * seg * 5;
+  unsigned long long* mask = mask_all + (int64_t)b * seg * col_blocks;
   const int row_start = blockIdx.y, col_start = blockIdx.x;
   if (row_start * 64 >= n || col_start * 64 >= n) return;
   const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
@@ -152,55 +163,59 @@ __global__ void nms_mask_kernel(int n_cap, const int* __restrict__ n_dev, float 
   }
 }
 
-// The host greedy loop of the reference (nms_kernel.cu:104-123) as a single-block device pass: no D2H.
-// Thread j keeps suppression word j in a register.  Per chunk of 64 boxes: (1) the 64 diagonal mask words are
-// fetched in parallel, (2) one thread resolves the intra-chunk greedy order with register bit-ops, (3) every thread
-// ORs the rows of the boxes kept in this chunk into its word (coalesced, independent loads).
-__global__ void __launch_bounds__(128) nms_reduce_kernel(int n_cap, const int* __restrict__ n_dev,
-                                                         const unsigned long long* __restrict__ mask, int col_blocks,
-                                                         int32_t* __restrict__ keep, int* __restrict__ nkeep) {
-  __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long s_cur, s_kept;
-  __shared__ int s_num;
-  const int n = n_dev ? min(*n_dev, n_cap) : n_cap;
+// The host greedy loop of the reference (nms_kernel.cu:104-123) as a device pass, one block per problem: no D2H.
+// The suppression words live in shared memory.  Per chunk of 64 boxes: (1) the 64 diagonal mask words are fetched in
+// parallel, (2) one thread resolves the intra-chunk greedy order (the only serial part), (3) 8 x 128 threads OR the
+// rows of the boxes kept in this chunk into the remaining words -- independent loads, one L2 round trip per chunk.
+__global__ void __launch_bounds__(1024) nms_reduce_kernel(NmsBatch nb, int seg, const int* __restrict__ n_dev,
+                                                          const unsigned long long* __restrict__ mask_all, int col_blocks,
+                                                          int32_t* __restrict__ keep_all, int* __restrict__ nkeep) {
+  __shared__ unsigned long long s_remv[128], diag[64];
+  __shared__ int s_rows[64];
+  __shared__ int s_nk, s_num;
+  const int b = blockIdx.x;
+  const int n = nms_count(nb, n_dev, b);
+  const unsigned long long* mask = mask_all + (int64_t)b * seg * col_blocks;
+  int32_t* keep = keep_all + (int64_t)b * seg;
   const int cb = (n + 63) / 64;
-  const int j = threadIdx.x;
-  unsigned long long remv = 0ULL;      // thread j < cb owns word j
-  if (j == 0) s_num = 0;
+  const int tid = threadIdx.x;
+  if (tid < 128) s_remv[tid] = 0ULL;
+  if (tid == 0) s_num = 0;
   __syncthreads();
   for (int c = 0; c < cb; ++c) {
-    if (j == c) s_cur = remv;
-    if (j < 64) {
-      const int i = c * 64 + j;
-      diag[j] = (i < n) ? mask[(int64_t)i * col_blocks + c] : 0ULL;
+    if (tid < 64) {
+      const int i = c * 64 + tid;
+      diag[tid] = (i < n) ? mask[(int64_t)i * col_blocks + c] : 0ULL;
     }
     __syncthreads();
-    if (j == 0) {
-      unsigned long long cur = s_cur, kept = 0ULL;
+    if (tid == 0) {
+      unsigned long long cur = s_remv[c];
       const int lim = min(64, n - c * 64);
-      int num = s_num;
+      int num = s_num, nk = 0;
       for (int i = 0; i < lim; ++i) {
         if (!((cur >> i) & 1ULL)) {
-          kept |= 1ULL << i;
           cur |= diag[i];
           keep[num++] = c * 64 + i;
+          s_rows[nk++] = c * 64 + i;
         }
       }
-      s_kept = kept;
+      s_nk = nk;
       s_num = num;
     }
     __syncthreads();
-    if (j > c && j < cb) {
-      unsigned long long kept = s_kept;
-      while (kept) {
-        const int i = __ffsll((long long)kept) - 1;
-        kept &= kept - 1;
-        remv |= mask[(int64_t)(c * 64 + i) * col_blocks + j];
+    {
+      const int j = tid & 127, r = tid >> 7;
+      if (j > c && j < cb) {
+        const int nk = s_nk;
+        unsigned long long acc = 0ULL;
+#pragma unroll 8
+        for (int q = r; q < nk; q += 8) acc |= mask[(int64_t)s_rows[q] * col_blocks + j];
+        if (acc) atomicOr(&s_remv[j], acc);
       }
     }
     __syncthreads();
   }
-  if (j == 0) *nkeep = s_num;
+  if (tid == 0) nkeep[b] = s_num;
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n_cap,
@@ -524,19 +539,32 @@ extern "C" int vps_rpn_decode(const float* scores_sorted, const int32_t* idx_sor
   return VPS_OK;
 }
 
-extern "C" int vps_nms(const float* dets, int n, const int* n_dev, float thr, int32_t* keep_idx, int* nkeep, void* ws,
-                       int64_t ws_bytes, void* stream) {
+extern "C" int vps_nms_batch(const float* dets, int nb, int seg, const int* ns, const int* n_dev, float thr,
+                             int32_t* keep_idx, int* nkeep, void* ws, int64_t ws_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (n <= 0) { cudaMemsetAsync(nkeep, 0, sizeof(int), st); return VPS_OK; }
-  const int col_blocks = (n + 63) / 64;
-  VPS_CHECK_ARG(ws_bytes >= (int64_t)n * col_blocks * 8, "nms: workspace too small");
-  VPS_CHECK_ARG(col_blocks <= 128, "nms: n %d too large (max 8192)", n);
-  dim3 grid(col_blocks, col_blocks);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(n, n_dev, thr, dets, (unsigned long long*)ws, col_blocks);
+  VPS_CHECK_ARG(nb >= 1 && nb <= 8 && seg >= 0, "nms_batch: nb %d (max 8)", nb);
+  NmsBatch b;
+  int nmax = 0;
+  for (int i = 0; i < 8; ++i) {
+    b.n[i] = i < nb ? ns[i] : 0;
+    VPS_CHECK_ARG(b.n[i] >= 0 && b.n[i] <= seg, "nms_batch: n[%d] = %d exceeds the segment %d", i, b.n[i], seg);
+    if (b.n[i] > nmax) nmax = b.n[i];
+  }
+  if (nmax <= 0) { cudaMemsetAsync(nkeep, 0, sizeof(int) * nb, st); return VPS_OK; }
+  const int col_blocks = (nmax + 63) / 64;
+  VPS_CHECK_ARG(ws_bytes >= (int64_t)nb * seg * col_blocks * 8, "nms: workspace too small");
+  VPS_CHECK_ARG(col_blocks <= 128, "nms: n %d too large (max 8192)", nmax);
+  dim3 grid(col_blocks, col_blocks, nb);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(b, seg, n_dev, thr, dets, (unsigned long long*)ws, col_blocks);
   VPS_CUDA_LAST("nms_mask");
-  nms_reduce_kernel<<<1, 128, 0, st>>>(n, n_dev, (const unsigned long long*)ws, col_blocks, keep_idx, nkeep);
+  nms_reduce_kernel<<<nb, 1024, 0, st>>>(b, seg, n_dev, (const unsigned long long*)ws, col_blocks, keep_idx, nkeep);
   VPS_CUDA_LAST("nms_reduce");
   return VPS_OK;
+}
+
+extern "C" int vps_nms(const float* dets, int n, const int* n_dev, float thr, int32_t* keep_idx, int* nkeep, void* ws,
+                       int64_t ws_bytes, void* stream) {
+  return vps_nms_batch(dets, 1, n, &n, n_dev, thr, keep_idx, nkeep, ws, ws_bytes, stream);
 }
 
 extern "C" int vps_gather_rows(const float* src, const int32_t* idx, int n, const int* n_dev, int width, float* dst,

@@ -186,14 +186,16 @@ __global__ void deform_im2col_kernel(vps::TV<const T> x, vps::TV<const TOF> off,
 template <typename TOF>
 __global__ void deform_im2col_bf16x8_kernel(vps::TV<const __nv_bfloat16> x, vps::TV<const TOF> off,
                                             vps::TV<__nv_bfloat16> cols, int64_t total) {
-  const int C = x.c, H = x.h, W = x.w, C8 = x.c / 8;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    int64_t t = i / C8;
-    const int k = (int)(t % 9); t /= 9;
-    const int xo = (int)(t % W); t /= W;
-    const int yo = (int)(t % H);
-    const int n = (int)(t / H);
+  const int C = x.c, H = x.h, W = x.w;
+  const uint32_t C8 = (uint32_t)x.c / 8u;
+  // 32-bit index arithmetic (host guarantees total < 2^31): 64-bit div/mod chains were the whole cost of this kernel
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
+    const uint32_t c8 = i % C8;
+    uint32_t t = i / C8;
+    const int k = (int)(t % 9u); t /= 9u;
+    const int xo = (int)(t % (uint32_t)W); t /= (uint32_t)W;
+    const int yo = (int)(t % (uint32_t)H);
+    const int n = (int)(t / (uint32_t)H);
     const TOF* op = off.p + off.off(n, yo, xo);
     const float oh = vps::ldf<TOF>(op + 2 * k), ow = vps::ldf<TOF>(op + 2 * k + 1);
     const float h = (float)(yo - 1 + k / 3) + oh;
@@ -333,6 +335,7 @@ extern "C" int vps_deform_im2col(const vps_tensor* x, const vps_tensor* offset, 
   if (x->dtype == VPS_BF16 && x->c % 8 == 0 && x->cs % 8 == 0 && cols->cs % 8 == 0 && ((uintptr_t)x->ptr & 15) == 0 &&
       ((uintptr_t)cols->ptr & 15) == 0) {
     const int64_t tot8 = total / 8;
+    VPS_CHECK_ARG(tot8 < (1ll << 31) - (148ll * 64 * 256), "deform_im2col: tensor too large for 32-bit indexing");
     int64_t blocks = (tot8 + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
     if (offset->dtype == VPS_F32)

@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(256) gn_stats_vec_kernel(vps::TV<const TI> x, 
       vps::ldv<TI, V>(x.p + ((int64_t)n * npix + pix) * x.cs + c0, v);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const int gi = (V > 1 && cg < V) ? (j / cg) : 0;      // cg < V only when V == 2 * cg
-        s[gi & 1] += v[j];
-        ss[gi & 1] += v[j] * v[j];
+        const int gi = (V > 1 && j >= cg) ? 1 : 0;            // cg < V only when V == 2 * cg (no runtime division)
+        s[gi] += v[j];
+        ss[gi] += v[j] * v[j];
       }
       if (++cnt == 64) {
         ds[0] += s[0]; ds[1] += s[1]; dss[0] += ss[0]; dss[1] += ss[1];
@@ -212,22 +212,33 @@ __global__ void __launch_bounds__(256) gn_stats_vec_kernel(vps::TV<const TI> x, 
   }
 }
 
+// mean / rstd of every (n, group) are finalised ONCE per block into shared memory (fp64 divides per element made this
+// kernel ALU-bound); the per-element expression (v - mean) * rstd * gamma + beta is unchanged.
 template <typename TI, typename TO, int V>
 __global__ void gn_apply_kernel(vps::TV<const TI> x, vps::TV<TO> y, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                 int relu) {
-  VPS_PIX_COORDS(y, V, c, xx, yy, n);
+  __shared__ float s_mean[64], s_rstd[64];
   const int cg = x.c / groups;
-  const double cnt = (double)x.h * x.w * cg;
+  {
+    const int n_blk = blockIdx.z;                    // pix_grid: z = image index
+    const double cnt = (double)x.h * x.w * cg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const double m = stats[((int64_t)n_blk * groups + g) * 2] / cnt;
+      const double var = stats[((int64_t)n_blk * groups + g) * 2 + 1] / cnt - m * m;
+      s_mean[g] = (float)m;
+      s_rstd[g] = rsqrtf((float)var + eps);
+    }
+  }
+  __syncthreads();
+  VPS_PIX_COORDS(y, V, c, xx, yy, n);
   float v[V];
   vps::ldv<TI, V>(x.p + x.off(n, yy, xx) + c, v);
+  const int g0 = c / cg;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    const int g = (c + j) / cg;
-    const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
-    const double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
-    const float rstd = rsqrtf((float)var + eps);
-    float o = (v[j] - (float)m) * rstd * gamma[c + j] + beta[c + j];
+    const int g = (V > 1 && cg < V) ? g0 + (j >= cg ? 1 : 0) : (cg % V == 0 ? g0 : (c + j) / cg);
+    float o = (v[j] - s_mean[g]) * s_rstd[g] * gamma[c + j] + beta[c + j];
     v[j] = relu ? fmaxf(o, 0.f) : o;
   }
   vps::stv<TO, V>(y.p + y.off(n, yy, xx) + c, v);
@@ -407,6 +418,7 @@ namespace { double* g_gn_stats = nullptr; int64_t g_gn_cap = 0; }
 extern "C" int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const float* gamma, const float* beta,
                              int groups, float eps, int relu, void* stream) {
   VPS_CHECK_ARG(x->c % groups == 0 && x->c == y->c && x->h == y->h && x->w == y->w, "groupnorm: shape");
+  VPS_CHECK_ARG(groups >= 1 && groups <= 64, "groupnorm: groups %d not in [1, 64]", groups);
   const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
   if (!total) return VPS_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -451,6 +451,8 @@ class RPNHead(_Prepared):
         seg = min(pre, post) if pre > 0 else post
         dets_cat = torch.zeros(nlev * seg, 5, device=dev)
         counts = torch.zeros(nlev, dtype=torch.int32, device=dev)
+        dets_all = torch.zeros(nlev * seg, 5, device=dev)          # level l: rows [l*seg, l*seg + ks[l])
+        ks = []
         for l, hd in enumerate(heads):
             _, h, w, _ = hd.shape
             n = h * w * A
@@ -463,13 +465,16 @@ class RPNHead(_Prepared):
             k = min(n, pre) if pre > 0 else n
             assert k <= seg or pre <= 0
             k = min(k, seg)
-            dets = torch.empty(k, 5, device=dev)
+            ks.append(k)
             ops.rpn_decode(s_sorted, i_sorted, k, hd[..., A:5 * A], self.anchor_strides[l], self.base_anchors[l],
-                           float(img_shape[0]), float(img_shape[1]), dets)
-            keep = torch.empty(k, dtype=torch.int32, device=dev)
-            nws = torch.empty(max(ops.nms_ws_bytes(k), 8), dtype=torch.uint8, device=dev)
-            ops.nms(dets, k, cfg['nms_thr'], keep, counts[l:l + 1], nws)
-            ops.gather_rows(dets, keep, k, 5, dets_cat[l * seg:l * seg + k], n_dev=counts[l:l + 1])
+                           float(img_shape[0]), float(img_shape[1]), dets_all[l * seg:l * seg + k])
+        # the per-level NMS of get_bboxes_single, all levels in one launch pair
+        keep = torch.empty(nlev * seg, dtype=torch.int32, device=dev)
+        nws = torch.empty(max(nlev * ops.nms_ws_bytes(seg), 8), dtype=torch.uint8, device=dev)
+        ops.nms_batch(dets_all, ks, seg, cfg['nms_thr'], keep, counts, nws)
+        for l in range(nlev):
+            ops.gather_rows(dets_all[l * seg:(l + 1) * seg], keep[l * seg:(l + 1) * seg], ks[l], 5,
+                            dets_cat[l * seg:l * seg + ks[l]], n_dev=counts[l:l + 1])
         ntot = nlev * seg
         proposals = torch.empty(max_num, 5, device=dev)
         rois = torch.empty(max_num, 5, device=dev)

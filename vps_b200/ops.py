@@ -335,6 +335,13 @@ def nms(dets, n, thr, keep_idx, nkeep, ws, n_dev=None):
                         C.c_int64(ws.numel() * ws.element_size()), stream()), "nms")
 
 
+def nms_batch(dets, ns, seg, thr, keep_idx, nkeep, ws, n_dev=None):
+    """len(ns) problems in one launch pair; problem b = rows [b*seg, b*seg+ns[b]) of dets."""
+    arr = (C.c_int * len(ns))(*ns)
+    check(lib().vps_nms_batch(_ptr(dets), len(ns), seg, arr, _ptr(n_dev), C.c_float(thr), _ptr(keep_idx), _ptr(nkeep), _ptr(ws),
+                              C.c_int64(ws.numel() * ws.element_size()), stream()), "nms_batch")
+
+
 def gather_rows(src, idx, n, width, dst, n_dev=None):
     check(lib().vps_gather_rows(_ptr(src), _ptr(idx), n, _ptr(n_dev), width, _ptr(dst), stream()), "gather_rows")
     return dst
