@@ -18,6 +18,10 @@ SHAPES = [
     (256, 256, 128, 256, 3, 1), (128, 128, 128, 256, 3, 1), (473, 256, 128, 256, 3, 1), (386, 2, 128, 256, 3, 1),
     (256, 256, 64, 128, 3, 1), (512, 512, 64, 128, 3, 1), (512, 512, 32, 64, 3, 1), (1024, 1024, 16, 32, 3, 1),
     (1024, 2, 16, 32, 3, 1), (256, 256, 14, 14, 3, 1),
+    # flat mode: 1x1 and strided
+    (64, 256, 256, 512, 1, 1), (256, 64, 256, 512, 1, 1), (128, 512, 128, 256, 1, 1), (1024, 256, 64, 128, 1, 1),
+    (256, 1024, 64, 128, 1, 1), (512, 2048, 32, 64, 1, 1), (2304, 256, 256, 512, 1, 1), (64, 128, 512, 1024, 5, 2),
+    (64, 64, 1024, 2048, 3, 2), (512, 512, 64, 128, 3, 2), (128, 256, 256, 512, 5, 2),
 ]
 iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 7
 dev = torch.device("cuda:0")

@@ -47,6 +47,7 @@ struct ConvTcParams {
   int a_stage_bytes;          // bytes of one A ring slot (multiple of 1024)
   int a_box_bytes;            // bytes one A TMA box delivers
   int rowg;                   // halo mode: 1 = one B ring slot holds the kw taps of a filter row (one barrier round per row)
+  int gsub;                   // flat (non-halo) mode: K steps per ring slot (one barrier round covers gsub steps)
   int nk_last;                // K16 slabs of the last channel chunk that hold real channels (the rest is zero padding)
   int total_tiles;
   long long* stats;           // optional [grid][8] clock counters (VPS_CONV_STATS=1), else NULL
@@ -427,8 +428,9 @@ struct Ring {
   __device__ __forceinline__ uint32_t tempty(int a) const { return bar_base + 8u * (4 * MAX_STAGES + 2 + a); }
 };
 
-template <bool HALO, bool ROWG, bool STATS>
-__device__ __forceinline__ void producer_loop(const ConvTcParams& p, const Ring& rg, const CUtensorMap* tmA,
+// ---- halo mode: one activation box per channel chunk (A ring), weights per tap or per filter row (B ring)
+template <bool ROWG, bool STATS>
+__device__ __forceinline__ void producer_halo(const ConvTcParams& p, const Ring& rg, const CUtensorMap* tmA,
                                               const CUtensorMap* tmB0, const CUtensorMap* tmB1, const CUtensorMap* tmB2,
                                               const CUtensorMap* tmB3, int lane) {
   const int bk = p.bk, kw = p.kw, cin_chunks = p.cin_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
@@ -446,34 +448,20 @@ __device__ __forceinline__ void producer_loop(const ConvTcParams& p, const Ring&
     const int img = m_idx / tiles_per_img;
     const int rem = m_idx - img * tiles_per_img;
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-    const int x_base = tx * p.tw * p.sw - p.pw_[prob];
-    const int y_base = ty * p.th * p.sh - p.ph_[prob];
+    const int x_base = tx * p.tw - p.pw_[prob];
+    const int y_base = ty * p.th - p.ph_[prob];
     const int n0 = n_idx * p.block_n;
     const CUtensorMap* tmB = prob == 0 ? tmB0 : (prob == 1 ? tmB1 : (prob == 2 ? tmB2 : tmB3));
     for (int cc = 0; cc < cin_chunks; ++cc) {
-      if (HALO) {
-        const long long t0 = STATS ? clock64() : 0;
-        mbar_wait(rg.aempty(as), aphase ^ 1);
-        if (STATS) st_a += clock64() - t0;
-        if (elect_one()) {
-          mbar_expect_tx(rg.afull(as), a_box_bytes);
-          tma_load_4d(rg.a_base + as * rg.a_stage_bytes, tmA, rg.afull(as), cc * bk, x_base, y_base, img);
-        }
-        if (++as == a_stages) { as = 0; aphase ^= 1; }
+      const long long t0 = STATS ? clock64() : 0;
+      mbar_wait(rg.aempty(as), aphase ^ 1);
+      if (STATS) st_a += clock64() - t0;
+      if (elect_one()) {
+        mbar_expect_tx(rg.afull(as), a_box_bytes);
+        tma_load_4d(rg.a_base + as * rg.a_stage_bytes, tmA, rg.afull(as), cc * bk, x_base, y_base, img);
       }
-      int r = 0, sx = 0;
+      if (++as == a_stages) { as = 0; aphase ^= 1; }
       for (int g = 0; g < ngrp; ++g) {
-        if (!HALO) {
-          const long long t0 = STATS ? clock64() : 0;
-          mbar_wait(rg.aempty(as), aphase ^ 1);
-          if (STATS) st_a += clock64() - t0;
-          if (elect_one()) {
-            mbar_expect_tx(rg.afull(as), a_box_bytes);
-            tma_load_4d(rg.a_base + as * rg.a_stage_bytes, tmA, rg.afull(as), cc * bk, x_base + sx, y_base + r, img);
-          }
-          if (++as == a_stages) { as = 0; aphase ^= 1; }
-          if (++sx == kw) { sx = 0; ++r; }
-        }
         const long long t1 = STATS ? clock64() : 0;
         mbar_wait(rg.bempty(bs), bphase ^ 1);
         if (STATS) st_b += clock64() - t1;
@@ -486,6 +474,54 @@ __device__ __forceinline__ void producer_loop(const ConvTcParams& p, const Ring&
     }
   }
   if (STATS && lane == 0) { p.stats[blockIdx.x * 8 + 0] = st_a; p.stats[blockIdx.x * 8 + 1] = st_b; }
+}
+
+// ---- flat mode (strided / 1x1 convolutions): K steps in (chunk, tap) order, gsub steps share one ring slot and one
+// barrier round (both operands arrive on the slot's `afull` barrier; the B barriers are unused)
+template <bool STATS>
+__device__ __forceinline__ void producer_flat(const ConvTcParams& p, const Ring& rg, const CUtensorMap* tmA,
+                                              const CUtensorMap* tmB0, const CUtensorMap* tmB1, const CUtensorMap* tmB2,
+                                              const CUtensorMap* tmB3, int lane) {
+  const int bk = p.bk, kw = p.kw, kh = p.kh, stages = p.a_stages, G = p.gsub;
+  const int T = p.cin_chunks * kh * kw;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes;
+  const uint32_t b_tile_bytes = (uint32_t)p.block_n * (uint32_t)bk * 2u;
+  int st = 0;
+  uint32_t phase = 0;
+  long long st_a = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int prob = tile / p.tiles_per_prob;
+    const int t_in = tile - prob * p.tiles_per_prob;
+    const int n_idx = t_in % p.n_tiles_n;
+    const int m_idx = t_in / p.n_tiles_n;
+    const int img = m_idx / tiles_per_img;
+    const int rem = m_idx - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int x_base = tx * p.tw * p.sw - p.pw_[prob];
+    const int y_base = ty * p.th * p.sh - p.ph_[prob];
+    const int n0 = n_idx * p.block_n;
+    const CUtensorMap* tmB = prob == 0 ? tmB0 : (prob == 1 ? tmB1 : (prob == 2 ? tmB2 : tmB3));
+    int cc = 0, r = 0, sx = 0;
+    for (int q0 = 0; q0 < T; q0 += G) {
+      const int cnt = min(G, T - q0);
+      const long long t0 = STATS ? clock64() : 0;
+      mbar_wait(rg.aempty(st), phase ^ 1);
+      if (STATS) st_a += clock64() - t0;
+      const uint32_t a_slot = rg.a_base + st * rg.a_stage_bytes, b_slot = rg.b_base + st * rg.b_stage_bytes;
+      if (elect_one()) mbar_expect_tx(rg.afull(st), (uint32_t)cnt * (a_box_bytes + b_tile_bytes));
+      __syncwarp();
+      for (int j = 0; j < cnt; ++j) {
+        if (elect_one()) {
+          tma_load_4d(a_slot + j * a_box_bytes, tmA, rg.afull(st), cc * bk, x_base + sx, y_base + r, img);
+          tma_load_3d(b_slot + j * b_tile_bytes, tmB, rg.afull(st), cc * bk, n0, r * kw + sx);
+        }
+        if (++sx == kw) { sx = 0; if (++r == kh) { r = 0; ++cc; } }
+      }
+      if (++st == stages) { st = 0; phase ^= 1; }
+    }
+  }
+  if (STATS && lane == 0) { p.stats[blockIdx.x * 8 + 0] = st_a; p.stats[blockIdx.x * 8 + 1] = 0; }
 }
 
 // the (up to) four K16 MMAs of one tap: 64 channels = one SWIZZLE_128B row; +2 in the (addr >> 4) field = 32 bytes
@@ -502,8 +538,8 @@ __device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint64_t a_hi, uint64
   }
 }
 
-template <bool HALO, bool ROWG, bool BK64, bool STATS>
-__device__ __forceinline__ void mma_loop(const ConvTcParams& p, const Ring& rg, uint32_t tmem_base, int lane) {
+template <bool ROWG, bool BK64, bool STATS>
+__device__ __forceinline__ void mma_halo(const ConvTcParams& p, const Ring& rg, uint32_t tmem_base, int lane) {
   constexpr uint32_t row_bytes = BK64 ? 128u : 32u;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N=block_n, M=128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
@@ -514,7 +550,7 @@ __device__ __forceinline__ void mma_loop(const ConvTcParams& p, const Ring& rg, 
   const uint32_t halo_pitch = (uint32_t)p.halo_w * row_bytes;
   const uint32_t tap_b_bytes = (uint32_t)p.block_n * row_bytes;
   // descriptor high words are loop constants; the low word is (smem address >> 4)
-  const uint64_t a_hi = make_smem_desc(0, BK64 ? 64 : 16, HALO ? halo_pitch : 8u * row_bytes);
+  const uint64_t a_hi = make_smem_desc(0, BK64 ? 64 : 16, halo_pitch);
   const uint64_t b_hi = make_smem_desc(0, BK64 ? 64 : 16, 8u * row_bytes);
   int as = 0, bs = 0, acc = 0;
   uint32_t aphase = 0, bphase = 0, acc_phase = 0;
@@ -529,25 +565,14 @@ __device__ __forceinline__ void mma_loop(const ConvTcParams& p, const Ring& rg, 
     uint32_t first = 0;
     for (int cc = 0; cc < cin_chunks; ++cc) {
       const int nk = cc == cin_chunks - 1 ? nk_last : 4;
-      uint32_t a_row = 0, a_tap = 0;
-      int a_cur = 0, sx = 0;
-      if (HALO) {
-        const long long t0 = STATS ? clock64() : 0;
-        mbar_wait(rg.afull(as), aphase);
-        if (STATS) st_a += clock64() - t0;
-        a_row = a_tap = rg.a_base + as * rg.a_stage_bytes;
-        a_cur = as;
-        if (++as == a_stages) { as = 0; aphase ^= 1; }
-      }
+      const long long t0 = STATS ? clock64() : 0;
+      mbar_wait(rg.afull(as), aphase);
+      if (STATS) st_a += clock64() - t0;
+      uint32_t a_row = rg.a_base + as * rg.a_stage_bytes, a_tap = a_row;
+      const int a_cur = as;
+      int sx = 0;
+      if (++as == a_stages) { as = 0; aphase ^= 1; }
       for (int g = 0; g < ngrp; ++g) {
-        if (!HALO) {
-          const long long t0 = STATS ? clock64() : 0;
-          mbar_wait(rg.afull(as), aphase);
-          if (STATS) st_a += clock64() - t0;
-          a_tap = rg.a_base + as * rg.a_stage_bytes;
-          a_cur = as;
-          if (++as == a_stages) { as = 0; aphase ^= 1; }
-        }
         const long long t1 = STATS ? clock64() : 0;
         mbar_wait(rg.bfull(bs), bphase);
         if (STATS) st_b += clock64() - t1;
@@ -565,17 +590,15 @@ __device__ __forceinline__ void mma_loop(const ConvTcParams& p, const Ring& rg, 
             issue_tap<BK64>(d_tmem, a_hi, b_hi, a_tap, b_addr, idesc, nk, first);
           }
           umma_commit(rg.bempty(bs));
-          if (!HALO || g == ngrp - 1) umma_commit(rg.aempty(a_cur));
+          if (g == ngrp - 1) umma_commit(rg.aempty(a_cur));
         }
         first = 1;
         if (++bs == b_stages) { bs = 0; bphase ^= 1; }
-        if (HALO) {
-          if (ROWG) {
-            a_row += halo_pitch;
-          } else {          // next tap: one pixel to the right, or the start of the next halo row
-            a_tap += row_bytes;
-            if (++sx == kw) { sx = 0; a_row += halo_pitch; a_tap = a_row; }
-          }
+        if (ROWG) {
+          a_row += halo_pitch;
+        } else {          // next tap: one pixel to the right, or the start of the next halo row
+          a_tap += row_bytes;
+          if (++sx == kw) { sx = 0; a_row += halo_pitch; a_tap = a_row; }
         }
       }
     }
@@ -585,6 +608,53 @@ __device__ __forceinline__ void mma_loop(const ConvTcParams& p, const Ring& rg, 
   }
   if (STATS && lane == 0) {
     p.stats[blockIdx.x * 8 + 2] = st_a; p.stats[blockIdx.x * 8 + 3] = st_b; p.stats[blockIdx.x * 8 + 4] = st_t;
+    p.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;
+  }
+}
+
+template <bool BK64, bool STATS>
+__device__ __forceinline__ void mma_flat(const ConvTcParams& p, const Ring& rg, uint32_t tmem_base, int lane) {
+  constexpr uint32_t row_bytes = BK64 ? 128u : 32u;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                         ((uint32_t)(BLOCK_M >> 4) << 24);
+  const int stages = p.a_stages, G = p.gsub, ntaps = p.kh * p.kw;
+  const int T = p.cin_chunks * ntaps;
+  const int q_last = T - ntaps;                     // steps >= q_last belong to the last channel chunk
+  const int nk_last = p.nk_last;
+  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes, b_tile_bytes = (uint32_t)p.block_n * row_bytes;
+  const uint64_t a_hi = make_smem_desc(0, BK64 ? 64 : 16, 8u * row_bytes);
+  const uint64_t b_hi = a_hi;
+  int st = 0, acc = 0;
+  uint32_t phase = 0, acc_phase = 0;
+  long long st_a = 0, st_t = 0;
+  const long long t_begin = STATS ? clock64() : 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const long long t2 = STATS ? clock64() : 0;
+    mbar_wait(rg.tempty(acc), acc_phase ^ 1);
+    if (STATS) st_t += clock64() - t2;
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+    for (int q0 = 0; q0 < T; q0 += G) {
+      const int cnt = min(G, T - q0);
+      const long long t0 = STATS ? clock64() : 0;
+      mbar_wait(rg.afull(st), phase);
+      if (STATS) st_a += clock64() - t0;
+      tc_fence_after();
+      const uint32_t a_slot = rg.a_base + st * rg.a_stage_bytes, b_slot = rg.b_base + st * rg.b_stage_bytes;
+      if (elect_one()) {
+        for (int j = 0; j < cnt; ++j)
+          issue_tap<BK64>(d_tmem, a_hi, b_hi, a_slot + j * a_box_bytes, b_slot + j * b_tile_bytes, idesc,
+                          q0 + j >= q_last ? nk_last : 4, (uint32_t)((q0 + j) != 0));
+        umma_commit(rg.aempty(st));
+      }
+      if (++st == stages) { st = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(rg.tfull(acc));
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (STATS && lane == 0) {
+    p.stats[blockIdx.x * 8 + 2] = st_a; p.stats[blockIdx.x * 8 + 3] = 0; p.stats[blockIdx.x * 8 + 4] = st_t;
     p.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;
   }
 }
@@ -599,7 +669,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t row_bytes = (uint32_t)p.bk * 2u;
   const uint32_t a_stage_bytes = (uint32_t)p.a_stage_bytes;
-  const uint32_t b_stage_bytes = (uint32_t)p.block_n * row_bytes * (p.rowg ? (uint32_t)p.kw : 1u);
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * row_bytes * (p.halo ? (p.rowg ? (uint32_t)p.kw : 1u) : (uint32_t)p.gsub);
   const uint32_t b_base = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
   const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
   // barrier slots (8 B each): afull, aempty, bfull, bempty [MAX_STAGES each], tmem_full[2], tmem_empty[2], tmem ptr
@@ -640,6 +710,11 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+  // tail of the previous kernel in the stream; no global memory is touched before the wait.  Our own dependents are
+  // released immediately -- they block at their own wait until this grid has completed and flushed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   Ring rg;
   rg.a_base = smem_base; rg.a_stage_bytes = a_stage_bytes; rg.b_base = b_base; rg.b_stage_bytes = b_stage_bytes;
@@ -647,22 +722,23 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const bool st = p.stats != nullptr;
   if (warp == 0) {
     // ===================== TMA producer =====================
-#define VPS_PROD(H, R) \
-    do { if (st) producer_loop<H, R, true>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); \
-         else producer_loop<H, R, false>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); } while (0)
-    if (p.halo) { if (p.rowg) VPS_PROD(true, true); else VPS_PROD(true, false); }
-    else VPS_PROD(false, false);
-#undef VPS_PROD
+#define VPS_ROLE(FN, ...) \
+    do { if (st) FN<__VA_ARGS__, true>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); \
+         else FN<__VA_ARGS__, false>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); } while (0)
+    if (p.halo) { if (p.rowg) VPS_ROLE(producer_halo, true); else VPS_ROLE(producer_halo, false); }
+    else { if (st) producer_flat<true>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane);
+           else producer_flat<false>(p, rg, &tmA, &tmB0, &tmB1, &tmB2, &tmB3, lane); }
+#undef VPS_ROLE
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-#define VPS_MMA(H, R, B) \
-    do { if (st) mma_loop<H, R, B, true>(p, rg, tmem_base, lane); else mma_loop<H, R, B, false>(p, rg, tmem_base, lane); } while (0)
+#define VPS_MMA(FN, ...) \
+    do { if (st) FN<__VA_ARGS__, true>(p, rg, tmem_base, lane); else FN<__VA_ARGS__, false>(p, rg, tmem_base, lane); } while (0)
     if (p.bk == 64) {
-      if (p.halo) { if (p.rowg) VPS_MMA(true, true, true); else VPS_MMA(true, false, true); }
-      else VPS_MMA(false, false, true);
+      if (p.halo) { if (p.rowg) VPS_MMA(mma_halo, true, true); else VPS_MMA(mma_halo, false, true); }
+      else VPS_MMA(mma_flat, true);
     } else {
-      if (p.halo) { if (p.rowg) VPS_MMA(true, true, false); else VPS_MMA(true, false, false); }
-      else VPS_MMA(false, false, false);
+      if (p.halo) { if (p.rowg) VPS_MMA(mma_halo, true, false); else VPS_MMA(mma_halo, false, false); }
+      else VPS_MMA(mma_flat, false);
     }
 #undef VPS_MMA
   } else {
@@ -836,7 +912,19 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
   // halo mode: one B ring slot = the kw taps of a filter row when that fits (<= 48 KB) -- one barrier round per row
   p.rowg = (halo && a->kw > 1 && a->kw * block_n * bk * 2 <= 48 * 1024) ? 1 : 0;
   p.nk_last = bk == 64 ? (a->cin - (p.cin_chunks - 1) * 64 + 15) / 16 : 1;
-  const int b_stage_bytes = block_n * bk * 2 * (p.rowg ? a->kw : 1);
+  // flat mode: gsub consecutive K steps share a ring slot (<= 48 KB of operands per barrier round, at most 4 steps)
+  p.gsub = 1;
+  if (!halo) {
+    const int step_bytes = p.a_box_bytes + block_n * bk * 2;
+    int g = (48 * 1024) / step_bytes;
+    const int T = p.cin_chunks * a->kh * a->kw;
+    if (g > 4) g = 4;
+    if (g > T) g = T;
+    if (g < 1) g = 1;
+    p.gsub = g;
+    p.a_stage_bytes = g * p.a_box_bytes;
+  }
+  const int b_stage_bytes = block_n * bk * 2 * (halo ? (p.rowg ? a->kw : 1) : p.gsub);
   if (halo) {
     p.a_stages = p.cin_chunks >= 3 ? 3 : 2;
     int bst = (200 * 1024 - p.a_stages * p.a_stage_bytes) / b_stage_bytes;
@@ -921,7 +1009,19 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
     cudaMemsetAsync(stats_buf, 0, sizeof(long long) * 8 * grid, (cudaStream_t)stream);
     p.stats = stats_buf;
   }
-  conv_igemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], p);
+  static int pdl_env = -1;
+  if (pdl_env < 0) { const char* e = getenv("VPS_PDL"); pdl_env = e ? atoi(e) : 1; }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel, tmA, tmB[0], tmB[1], tmB[2], tmB[3], p);
+    if (le != cudaSuccess) { vps::set_error("conv2d_tc: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
+  }
   VPS_CUDA_LAST("conv_igemm_tc_kernel");
   if (stats_env) {
     static long long h[8 * 1024];
@@ -930,9 +1030,9 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
     double m[8] = {0};
     for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / grid;
     const int tiles_cta = (p.total_tiles + grid - 1) / grid;
-    fprintf(stderr, "conv_tc stats %dx%d %d->%d @%dx%d halo=%d/%d bn=%d bk=%d stages a%d b%d tiles/cta %d steps/tile %d | clk/CTA: total %.0f  "
+    fprintf(stderr, "conv_tc stats %dx%d %d->%d @%dx%d halo=%d/%d g%d bn=%d bk=%d stages a%d b%d tiles/cta %d steps/tile %d | clk/CTA: total %.0f  "
             "prod wait Aempty %.0f Bempty %.0f | mma wait Afull %.0f Bfull %.0f tmem-empty %.0f | epi wait tfull %.0f work %.0f\n",
-            a->kh, a->kw, a->cin, a->cout, a->oh, a->ow, p.halo, p.rowg, block_n, bk, p.a_stages, p.b_stages, tiles_cta,
+            a->kh, a->kw, a->cin, a->cout, a->oh, a->ow, p.halo, p.rowg, p.gsub, block_n, bk, p.a_stages, p.b_stages, tiles_cta,
             a->kh * a->kw * p.cin_chunks, m[5], m[0], m[1], m[2], m[3], m[4], m[6], m[7]);
   }
   return VPS_OK;
