@@ -174,6 +174,14 @@ int vps_tcea_combine(const vps_tensor* fea, const vps_tensor* att, const vps_ten
                      const vps_tensor* out, void* stream);
 
 /* ---- DCNv1 ---------------------------------------------------------------------------------- */
+/* Fused DCNv1 forward (deform_conv.py:15-87 -> deform_conv_cuda.cpp forward, deformable_im2col + GEMM) for the
+ * configuration the FuseTrack path uses: 3x3, stride 1, pad 1, dilation 1, 1 group, 1 deformable group, no bias.
+ * x bf16 NHWC (cin %% 64 == 0), offset f32 NHWC [.., >= 18] = (dy, dx) per tap, w = vps_pack_weights_tc layout of the
+ * OIHW kernel (cin_gran 64), y bf16 or f32 NHWC with cout <= 256 channels.  The sampled columns go straight into the
+ * tensor-core operand ring in shared memory; same bf16 columns as vps_deform_im2col + vps_conv2d_tc (1x1), summed over
+ * K chunk-major instead of tap-major (results agree to one bf16 rounding). */
+int vps_deform_conv_tc(const vps_tensor* x, const vps_tensor* offset, const void* w, int cout, const vps_tensor* y,
+                       void* stream);
 /* deformable_im2col (deform_conv_cuda_kernel.cu:83-113,189-242), 3x3 stride 1 pad 1 dil 1,
  * deformable_group 1.  offset NHWC [n,h,w,18] (ch 2k = dy, 2k+1 = dx); cols NHWC [n,h,w,9*c] (k-major). */
 int vps_deform_im2col(const vps_tensor* x, const vps_tensor* offset, const vps_tensor* cols, void* stream);
@@ -272,12 +280,13 @@ int vps_mask_removal(const float* boxes, const int32_t* order, int k, const int*
 /* final fusion (SegTerm unary_logits.py:81-108, paste mask_removal.py:86, argmax
  * panoptic_fusetrack.py:588-593): per full-resolution pixel, fcn_output = bilinear x4 of fcn_score
  * (upsnetFPN.py:59,80) computed in registers; pano_out = argmax over [stuff(num_stuff) | kept
- * instances (seg term + pasted mask logit)], sem_out = argmax over all classes; int64 [H,W] each.
+ * instances (seg term + pasted mask logit)], sem_out = argmax over all classes; [H,W] each, stored as int64
+ * (label_bytes 8, the dtype torch.max returns in the reference) or uint8 (label_bytes 1, same values, 8x less D2H).
  * dummy != 0: the MaskROI "no detection" result (one all-zero instance channel). */
 int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes, const int32_t* cls_idx,
                       const float* mask_logit, int msize, const int32_t* keep_sorted, const int* nkeep_dev,
-                      int kcap, int num_stuff, int dummy, int H, int W, int64_t* pano_out, int64_t* sem_out,
-                      void* stream);
+                      int kcap, int num_stuff, int dummy, int H, int W, void* pano_out, void* sem_out,
+                      int label_bytes, void* stream);
 
 #ifdef __cplusplus
 }

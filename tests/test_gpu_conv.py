@@ -121,3 +121,24 @@ def test_deconv4x4_as_phase_convs(cuda):
         got = y.cpu().permute(0, 3, 1, 2)
         err = (got - ref).abs().max().item()
         assert err <= tol * max(1.0, ref.abs().max().item()), (dtype, err)
+
+
+@pytest.mark.parametrize("cin,h,w", [(3, 33, 47), (12, 32, 64), (6, 17, 30)])
+def test_stem_7x7s2_space_to_depth(cuda, cin, h, w):
+    """StemConv7x7s2 (space-to-depth + 4x4 stride-1 tensor-core conv) == the 7x7 / stride 2 / pad 3 convolution it replaces
+    (resnet.py conv1, FlowNetC/S conv1), odd and even sizes."""
+    from vps_b200 import ops
+    from vps_b200.layers import StemConv7x7s2
+    g = torch.Generator().manual_seed(100 + cin)
+    x = torch.randn(1, cin, h, w, generator=g)
+    wt = torch.randn(64, cin, 7, 7, generator=g) / (cin * 49) ** 0.5
+    b = torch.randn(64, generator=g)
+    ref = F.relu(F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), b, stride=2, padding=3))
+    stem = StemConv7x7s2(wt.to(cuda), b.to(cuda), act=ops.ACT_RELU)
+    xd = _nhwc(x, torch.bfloat16).to(cuda)[..., :cin]
+    y = stem(xd, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    got = y.cpu().permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item()), "max err %g" % err

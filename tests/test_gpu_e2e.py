@@ -126,3 +126,36 @@ def test_cuda_graph_replay_equals_eager(models):
     for e, g in zip(outs[False], outs[True]):
         for x, y in zip(e, g):
             assert torch.equal(x, y)
+
+
+def test_clip_runner_equals_direct_calls(models):
+    """ClipRunner (prefetching clip loop, uint8 label maps downloaded on a copy stream) returns exactly what direct
+    simple_test calls return for the same clip (int64 maps), including the tracker ids carried across frames."""
+    from vps_b200.runner import ClipRunner
+    _, prod = models
+    prod.precision = "fp32"
+    H, W = 128, 256
+    frames = [make_pair(H, W, seed=s) for s in (5, 6, 7, 8, 9)]
+    metas = [meta(10001 + f, H, W) for f in range(len(frames))]
+    prod.label_dtype = torch.int64
+    prod.reset_tracker()
+    direct = []
+    for (a, b), m in zip(frames, metas):
+        r = prod.simple_test(a.cuda(), [m], ref_img=[b.cuda()])
+        direct.append((r[2]["panoptic_outputs"].cpu().clone(), r[2]["fcn_outputs"].cpu().clone(),
+                       r[2]["panoptic_det_obj_ids"].cpu().clone(), r[2]["panoptic_cls_inds"].cpu().clone()))
+    try:
+        prod.label_dtype = torch.uint8
+        prod.reset_tracker()
+        pinned = [(a.pin_memory(), b.pin_memory()) for a, b in frames]
+        got = []
+        for r in ClipRunner(prod, "cuda:0").run(pinned, metas):
+            assert r[2]["panoptic_outputs"].dtype == torch.uint8 and not r[2]["panoptic_outputs"].is_cuda
+            got.append((r[2]["panoptic_outputs"].clone(), r[2]["fcn_outputs"].clone(),
+                        r[2]["panoptic_det_obj_ids"].cpu().clone(), r[2]["panoptic_cls_inds"].cpu().clone()))
+    finally:
+        prod.label_dtype = torch.int64
+    assert len(got) == len(direct)
+    for d, g in zip(direct, got):
+        assert torch.equal(d[0], g[0].long()) and torch.equal(d[1], g[1].long())
+        assert torch.equal(d[2], g[2]) and torch.equal(d[3], g[3])

@@ -142,6 +142,39 @@ def test_deform_im2col_and_gemm(cuda):
     assert close(to_nchw(y), ref, 2e-5)
 
 
+def test_deform_conv_tc_fused(cuda):
+    """vps_deform_conv_tc (sampling fused into the tensor-core operand ring) vs vps_deform_im2col + 1x1 GEMM (same bf16
+    columns, different fp32 accumulation order over K: chunk-major vs tap-major -> equal up to one bf16 rounding), and
+    vs the oracle DCNv1 (deform_conv_cuda forward) on bf16-representable operands; ragged tiles, offsets that leave the
+    image, two images."""
+    from oracle import ops as O
+    from vps_b200 import ops
+    from vps_b200.layers import Conv
+    g = torch.Generator().manual_seed(15)
+    for (N, C, Co, H, W) in [(1, 128, 128, 19, 37), (2, 256, 256, 12, 20), (1, 64, 32, 8, 16)]:
+        x = torch.randn(N, C, H, W, generator=g).bfloat16().float()
+        off = torch.randn(N, 18, H, W, generator=g) * 3.0
+        off[:, :, 0, :] -= 4.0                       # some samples fall outside the image
+        w = (torch.randn(Co, C, 3, 3, generator=g) / (C * 9) ** 0.5).bfloat16().float()
+        ref = O.deform_conv(x, off, w)
+        xd = to_nhwc(x).bfloat16()
+        od = to_nhwc(off)
+        pk = ops.PackedConv(w.cuda(), None)
+        y = torch.full((N, H, W, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.deform_conv_tc(xd, od, pk, y)
+        cols = torch.empty(N, H, W, 9 * C, dtype=torch.bfloat16, device="cuda")
+        ops.deform_im2col(xd, od, cols)
+        w1 = w.permute(0, 2, 3, 1).reshape(Co, 9 * C, 1, 1).contiguous().cuda()
+        y2 = Conv(w1, None)(cols)
+        torch.cuda.synchronize()
+        assert not torch.isnan(y.float()).any()
+        scale = max(1.0, float(y2.float().abs().max()))
+        assert float((y.float() - y2.float()).abs().max()) <= 2.0 ** -7 * scale, "fused vs im2col + GEMM"
+        assert float((y.float() != y2.float()).float().mean()) < 0.05          # almost all outputs are bit-identical
+        got = y.float().permute(0, 3, 1, 2).cpu()
+        assert float((got - ref).abs().max()) <= 2e-2 * max(1.0, float(ref.abs().max()))
+
+
 def test_roi_align_multilevel(cuda):
     from oracle.model import roi_extract
     from vps_b200 import ops

@@ -355,9 +355,10 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
 // ---------------------------------------------------------------- epilogue role (warps 2..9)
 // warp -> TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter take alternate
 // 32-column chunks.  Two register sets: the next chunk's tcgen05.ld is in flight while the current one is processed.
-template <int ACT>
+template <int ACT, int GROUPS = NUM_EPI_WARPS / 4>
 __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               int warp, int lane) {
+  constexpr int CSTEP = 32 * GROUPS;      // the GROUPS warps of a TMEM lane quarter take alternate 32-column chunks
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
   const int row = q * 32 + lane;
@@ -391,12 +392,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, uint32_t tm
     if (c0 < p.block_n) tmem_ld32(t_row + (uint32_t)c0, ra);
     while (c0 < p.block_n) {
       tmem_ld_wait();
-      const int c1 = c0 + 64;
+      const int c1 = c0 + CSTEP;
       if (c1 < p.block_n) tmem_ld32(t_row + (uint32_t)c1, rb);
       if (valid && nbase + c0 < nlim) epi_chunk<ACT>(p, ra, pix, nbase + c0, nlim);
       if (c1 >= p.block_n) break;
       tmem_ld_wait();
-      const int c2 = c1 + 64;
+      const int c2 = c1 + CSTEP;
       if (c2 < p.block_n) tmem_ld32(t_row + (uint32_t)c2, ra);
       if (valid && nbase + c1 < nlim) epi_chunk<ACT>(p, rb, pix, nbase + c1, nlim);
       c0 = c2;
@@ -761,6 +762,186 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+
+// ---------------------------------------------------------------- fused deformable convolution (DCNv1, 3x3, pad 1)
+// Same implicit GEMM, but the A tile of a K step is not a TMA box: eight producer warps bilinearly sample the input
+// at the learned offsets (deform_conv_cuda_kernel.cu: deformable_im2col) straight into the SWIZZLE_128B operand slot,
+// so the 9x column matrix is never written to HBM.  K steps run chunk-major / tap-minor: for one 64-channel chunk the
+// nine taps of a tile touch the same ~(th+2) x (tw+2) x 128 B of input, which stays in L1.  Per tile the sampling
+// set-up of every (pixel, tap) -- 4 corner element offsets + 4 weights -- is computed once into shared memory.
+constexpr int DCN_GATHER_WARPS = 16;     // sampling is ALU-issue bound: 4 producer warps per SM sub-partition
+constexpr int DCN_EPI_WARPS = 4;
+constexpr int DCN_THREADS = 64 + 32 * DCN_EPI_WARPS + 32 * DCN_GATHER_WARPS;
+constexpr int DCN_SETUP_BYTES = 9 * BLOCK_M * 32;
+
+struct DcnParams {
+  const __nv_bfloat16* x;
+  const float* off;
+  int x_cs, off_cs, H, W;
+};
+
+__device__ __forceinline__ void dcn_gather_loop(const ConvTcParams& p, const DcnParams& d, const Ring& rg, uint32_t setup_base,
+                                                int gtid) {
+  const int stages = p.a_stages, cin_chunks = p.cin_chunks;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int H = d.H, W = d.W;
+  int st = 0;
+  uint32_t phase = 0;
+  const int j = gtid & 7;                    // 16-byte channel chunk of the 128-byte row
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int img = tile / tiles_per_img;
+    const int rem = tile - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    // ---- sampling set-up of all (tap, pixel) pairs of this tile
+    for (int item = gtid; item < 9 * BLOCK_M; item += 32 * DCN_GATHER_WARPS) {
+      const int k = item >> 7, r = item & (BLOCK_M - 1);
+      const int ty_in = r / p.tw, tx_in = r - ty_in * p.tw;
+      const int yo = ty * p.th + ty_in, xo = tx * p.tw + tx_in;
+      float wts[4] = {0.f, 0.f, 0.f, 0.f};
+      int offs[4] = {0, 0, 0, 0};
+      if (yo < H && xo < W) {
+        const float* op = d.off + ((int64_t)(img * H + yo) * W + xo) * d.off_cs;
+        const float oh = __ldg(op + 2 * k), ow = __ldg(op + 2 * k + 1);
+        const float h = (float)(yo - 1 + k / 3) + oh;
+        const float w = (float)(xo - 1 + k % 3) + ow;
+        if (h > -1.f && w > -1.f && h < (float)H && w < (float)W) {
+          const int hl = (int)floorf(h), wl = (int)floorf(w);
+          const int hh_ = hl + 1, wh_ = wl + 1;
+          const float lh = h - (float)hl, lw = w - (float)wl;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const int base = img * H;
+          if (hl >= 0 && wl >= 0) { wts[0] = hh * hw; offs[0] = ((base + hl) * W + wl) * d.x_cs; }
+          if (hl >= 0 && wh_ <= W - 1) { wts[1] = hh * lw; offs[1] = ((base + hl) * W + wh_) * d.x_cs; }
+          if (hh_ <= H - 1 && wl >= 0) { wts[2] = lh * hw; offs[2] = ((base + hh_) * W + wl) * d.x_cs; }
+          if (hh_ <= H - 1 && wh_ <= W - 1) { wts[3] = lh * lw; offs[3] = ((base + hh_) * W + wh_) * d.x_cs; }
+        }
+      }
+      const uint32_t sa = setup_base + (uint32_t)item * 32u;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(wts[0]), "f"(wts[1]), "f"(wts[2]), "f"(wts[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16u), "r"(offs[0]), "r"(offs[1]), "r"(offs[2]), "r"(offs[3]) : "memory");
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * DCN_GATHER_WARPS) : "memory");
+    // ---- K steps: chunk-major, tap-minor
+    for (int cc = 0; cc < cin_chunks; ++cc) {
+      const __nv_bfloat16* xc = d.x + cc * 64 + j * 8;
+      for (int k = 0; k < 9; ++k) {
+        mbar_wait(rg.aempty(st), phase ^ 1);
+        const uint32_t a_slot = rg.a_base + st * rg.a_stage_bytes;
+        constexpr int ROWS_PER_PASS = 32 * DCN_GATHER_WARPS / 8;       // 8 lanes (16-byte chunks) per pixel row
+#pragma unroll
+        for (int i = 0; i < BLOCK_M / ROWS_PER_PASS; ++i) {
+          const int r = (gtid >> 3) + ROWS_PER_PASS * i;
+          const uint32_t sa = setup_base + (uint32_t)(k * BLOCK_M + r) * 32u;
+          float w0, w1, w2, w3;
+          int o0, o1, o2, o3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3) : "r"(sa));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(sa + 16u));
+          const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(xc + o0));
+          const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(xc + o1));
+          const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(xc + o2));
+          const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(xc + o3));
+          const float wq[4] = {w0, w1, w2, w3};
+          const uint4 qs[4] = {q0, q1, q2, q3};
+          float acc[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {           // corners outside the image carry weight 0 (branch-free: finite inputs)
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&qs[q]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(b2[t]);
+              acc[2 * t] += wq[q] * f.x;
+              acc[2 * t + 1] += wq[q] * f.y;
+            }
+          }
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __nv_bfloat162 b = __floats2bfloat162_rn(acc[2 * t], acc[2 * t + 1]);
+            pk[t] = *reinterpret_cast<uint32_t*>(&b);
+          }
+          const uint32_t da = a_slot + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(da), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+        mbar_arrive(rg.afull(st));
+        if (++st == stages) { st = 0; phase ^= 1; }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * DCN_GATHER_WARPS) : "memory");   // set-up cache is rewritten next tile
+  }
+}
+
+__global__ void __launch_bounds__(DCN_THREADS, 1)
+dcn_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const DcnParams d) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  Ring rg;
+  rg.a_base = smem_base; rg.a_stage_bytes = (uint32_t)p.a_stage_bytes;
+  rg.b_base = smem_base + (uint32_t)p.a_stages * rg.a_stage_bytes;
+  rg.b_stage_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t setup_base = rg.b_base + (uint32_t)p.a_stages * rg.b_stage_bytes;
+  rg.bar_base = setup_base + DCN_SETUP_BYTES;
+  const uint32_t tmem_slot = rg.bar_base + 8u * (4 * MAX_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(rg.afull(s), 1 + 32 * DCN_GATHER_WARPS);     // weight TMA (expect_tx arrival) + every gather thread
+      mbar_init(rg.aempty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(rg.tfull(a), 1);
+      mbar_init(rg.tempty(a), 32 * DCN_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // weight producer: one {64 ch, block_n, 1 tap} box per K step, completing on the step's `afull` barrier
+    const int stages = p.a_stages;
+    int st = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int cc = 0; cc < p.cin_chunks; ++cc) {
+        for (int k = 0; k < 9; ++k) {
+          mbar_wait(rg.aempty(st), phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(rg.afull(st), rg.b_stage_bytes);
+            tma_load_3d(rg.b_base + st * rg.b_stage_bytes, &tmB, rg.afull(st), cc * 64, 0, k);
+          }
+          if (++st == stages) { st = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    mma_flat<true, false>(p, rg, tmem_base, lane);
+  } else if (warp < 2 + DCN_EPI_WARPS) {
+    epilogue_loop<VPS_ACT_NONE, DCN_EPI_WARPS / 4>(p, tmem_base, rg.tfull(0), rg.tempty(0), warp, lane);
+  } else {
+    dcn_gather_loop(p, d, rg, setup_base, (int)threadIdx.x - 32 * (2 + DCN_EPI_WARPS));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- weight packing
 // dst[co][ (r*kw+s)*cin_pad + ci ] (bf16), zero padded; src OIHW (or IOHW when transposed)
 __global__ void pack_weights_tc_kernel(const float* __restrict__ src, const float* __restrict__ scale,
@@ -1039,3 +1220,93 @@ extern "C" int vps_conv2d_tc_multi(const vps_conv_args* args, int nprob, void* s
 }
 
 extern "C" int vps_conv2d_tc(const vps_conv_args* a, void* stream) { return vps_conv2d_tc_multi(a, 1, stream); }
+
+
+// Fused DCNv1 3x3 / stride 1 / pad 1 / dilation 1 / 1 deformable group (deform_conv.py:15-87 forward):
+// x bf16 NHWC, offset f32 NHWC [.., 18] = (dy, dx) per tap, w = vps_pack_weights_tc layout of the [cout, cin, 3, 3]
+// kernel (cin % 64 == 0, cout <= 256), y bf16 / f32 NHWC.  No bias (the reference's DeformConv has none).
+extern "C" int vps_deform_conv_tc(const vps_tensor* x, const vps_tensor* offset, const void* w, int cout, const vps_tensor* y,
+                                  void* stream) {
+  VPS_CHECK_ARG(x->dtype == VPS_BF16 && offset->dtype == VPS_F32 && offset->c >= 18, "deform_conv_tc: dtypes");
+  VPS_CHECK_ARG(x->c % 64 == 0 && x->cs % 8 == 0 && ((uintptr_t)x->ptr & 15) == 0, "deform_conv_tc: x must have cin %% 64 == 0");
+  VPS_CHECK_ARG(offset->n == x->n && offset->h == x->h && offset->w == x->w && y->n == x->n && y->h == x->h && y->w == x->w &&
+                    y->c == cout, "deform_conv_tc: shapes");
+  VPS_CHECK_ARG((int64_t)x->n * x->h * x->w * x->cs < (1ll << 31), "deform_conv_tc: tensor too large for 32-bit offsets");
+  const int cout_pad = (cout + 15) / 16 * 16;
+  VPS_CHECK_ARG(cout_pad <= 256 && ((uintptr_t)w & 15) == 0, "deform_conv_tc: cout %d > 256", cout);
+  auto encode = get_encode();
+  if (!encode) { vps::set_error("cuTensorMapEncodeTiled unavailable"); return VPS_E_CUDA; }
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) { vps::set_error("no device"); return VPS_E_NODEV; }
+  }
+  ConvTcParams p = {};
+  p.bk = 64; p.nprob = 1;
+  p.n_img = x->n; p.oh = x->h; p.ow = x->w;
+  int best_tw = 16; int64_t best_area = -1;
+  const int cands[5] = {16, 8, 32, 64, 128};
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cands[i], th = 128 / tw;
+    const int64_t area = (int64_t)vps::cdiv(x->w, tw) * tw * vps::cdiv(x->h, th) * th;
+    if (best_area < 0 || area < best_area) { best_area = area; best_tw = tw; }
+  }
+  p.tw = best_tw; p.th = 128 / best_tw;
+  p.tiles_x = vps::cdiv(x->w, p.tw); p.tiles_y = vps::cdiv(x->h, p.th);
+  p.n_tiles_n = 1; p.block_n = cout_pad;
+  p.kh = p.kw = 3; p.sh = p.sw = 1; p.ph = p.pw = 1;
+  p.cin_chunks = x->c / 64;
+  p.gsub = 1; p.nk_last = 4; p.halo = 0; p.rowg = 0;
+  p.a_box_bytes = BLOCK_M * 128; p.a_stage_bytes = p.a_box_bytes;
+  const int stage_bytes = p.a_stage_bytes + cout_pad * 128;
+  int stages = (200 * 1024 - DCN_SETUP_BYTES) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  VPS_CHECK_ARG(stages >= 2, "deform_conv_tc: ring does not fit");
+  p.a_stages = p.b_stages = stages;
+  p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x;
+  p.total_tiles = p.tiles_per_prob;
+  p.y = y->ptr; p.y_h = y->h; p.y_w = y->w; p.y_cs = y->cs; p.y_dtype = y->dtype;
+  const int esz = y->dtype == VPS_BF16 ? 2 : 4;
+  p.y_vec = (((uintptr_t)y->ptr & 15) == 0) && ((y->cs * esz) % 16 == 0);
+  if (p.y_vec && (((uintptr_t)y->ptr & 31) == 0) && ((y->cs * esz) % 32 == 0)) p.y_vec = 2;
+  p.oy_mul = p.ox_mul = 1;
+  p.res = nullptr; p.bias = nullptr; p.cout = cout; p.act = VPS_ACT_NONE; p.slope = 0.f; p.out_scale = 1.f;
+  p.stats = nullptr;
+  if (p.total_tiles == 0) return VPS_OK;
+  DcnParams d;
+  d.x = (const __nv_bfloat16*)x->ptr; d.off = (const float*)offset->ptr; d.x_cs = x->cs; d.off_cs = offset->cs;
+  d.H = x->h; d.W = x->w;
+  CUtensorMap tmB;
+  {
+    const cuuint64_t K = (cuuint64_t)9 * x->c;
+    cuuint64_t dims[3] = {(cuuint64_t)x->c, (cuuint64_t)cout_pad, 9};
+    cuuint64_t strides[2] = {K * 2, (cuuint64_t)x->c * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)cout_pad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vps::set_error("deform_conv_tc: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
+  }
+  const int smem = stages * stage_bytes + DCN_SETUP_BYTES + 1024 + 8 * (4 * MAX_STAGES + 8);
+  static bool smem_set = false;
+  if (!smem_set) {
+    if (cudaFuncSetAttribute(dcn_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      vps::set_error("deform_conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(cudaGetLastError()));
+      return VPS_E_CUDA;
+    }
+    smem_set = true;
+  }
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(DCN_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, dcn_igemm_tc_kernel, tmB, p, d);
+  if (le != cudaSuccess) { vps::set_error("deform_conv_tc: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
+  VPS_CUDA_LAST("dcn_igemm_tc_kernel");
+  return VPS_OK;
+}

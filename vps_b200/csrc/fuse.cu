@@ -206,12 +206,11 @@ __global__ void fuse_prepare_kernel(const float* __restrict__ boxes, const int32
   ip->px0[j] = r.x_0; ip->px1[j] = r.x_1; ip->py0[j] = r.y_0; ip->py1[j] = r.y_1;
 }
 
-template <typename T>
+template <typename T, typename TL>
 __global__ void __launch_bounds__(256) panoptic_fuse_kernel(vps::TV<const T> score, const float* __restrict__ mask_logit,
                                                             int ms, const InstParams* __restrict__ ipg,
                                                             const int* __restrict__ ninst_dev, int num_stuff, int dummy,
-                                                            int H, int W, int64_t* __restrict__ pano,
-                                                            int64_t* __restrict__ sem) {
+                                                            int H, int W, TL* __restrict__ pano, TL* __restrict__ sem) {
   __shared__ InstParams ip;
   {
     const int* src = (const int*)ipg;
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(256) panoptic_fuse_kernel(vps::TV<const T> sco
     float bs = fo[0]; int bsi = 0;
 #pragma unroll
     for (int c = 1; c < 24; ++c) if (c < NC && fo[c] > bs) { bs = fo[c]; bsi = c; }
-    sem[i] = bsi;
+    sem[i] = (TL)bsi;
     // panoptic argmax over [stuff | instances]
     float bp = fo[0]; int bpi = 0;
 #pragma unroll
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(256) panoptic_fuse_kernel(vps::TV<const T> sco
         if (v > bp) { bp = v; bpi = num_stuff + j; }
       }
     }
-    pano[i] = bpi;
+    pano[i] = (TL)bpi;
   }
 }
 
@@ -320,9 +319,10 @@ extern "C" int vps_mask_removal(const float* boxes, const int32_t* order, int k,
 
 extern "C" int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes, const int32_t* cls_idx,
                                  const float* mask_logit, int msize, const int32_t* keep_sorted, const int* nkeep_dev,
-                                 int kcap, int num_stuff, int dummy, int H, int W, int64_t* pano_out, int64_t* sem_out,
-                                 void* stream) {
+                                 int kcap, int num_stuff, int dummy, int H, int W, void* pano_out, void* sem_out,
+                                 int label_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  VPS_CHECK_ARG(label_bytes == 8 || (label_bytes == 1 && num_stuff + kcap <= 255), "panoptic_fuse: label_bytes %d", label_bytes);
   VPS_CHECK_ARG(fcn_score->c <= 24 && kcap <= MAX_INST && fcn_score->n == 1, "panoptic_fuse: args (c %d kcap %d)", fcn_score->c, kcap);
   if (!g_ip) {
     if (cudaMalloc(&g_ip, sizeof(InstParams)) != cudaSuccess || cudaMalloc(&g_ninst, sizeof(int)) != cudaSuccess) {
@@ -336,9 +336,15 @@ extern "C" int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes
     fuse_prepare_kernel<<<1, MAX_INST, 0, st>>>(boxes, cls_idx, keep_sorted, nkeep_dev, kcap, num_stuff, H, W, g_ip, g_ninst);
     VPS_CUDA_LAST("fuse_prepare");
   }
-  VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T><<<148 * 4, 256, 0, st>>>(
-                                          vps::tv<const T>(*fcn_score), mask_logit, msize, g_ip, g_ninst, num_stuff, dummy, H,
-                                          W, pano_out, sem_out)));
+  if (label_bytes == 8) {
+    VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T, int64_t><<<148 * 4, 256, 0, st>>>(
+                                            vps::tv<const T>(*fcn_score), mask_logit, msize, g_ip, g_ninst, num_stuff, dummy,
+                                            H, W, (int64_t*)pano_out, (int64_t*)sem_out)));
+  } else {
+    VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T, uint8_t><<<148 * 4, 256, 0, st>>>(
+                                            vps::tv<const T>(*fcn_score), mask_logit, msize, g_ip, g_ninst, num_stuff, dummy,
+                                            H, W, (uint8_t*)pano_out, (uint8_t*)sem_out)));
+  }
   VPS_CUDA_LAST("panoptic_fuse");
   return VPS_OK;
 }

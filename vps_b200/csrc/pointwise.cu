@@ -130,6 +130,31 @@ __global__ void space_to_depth2_kernel(vps::TV<const TI> x, vps::TV<TO> y) {
   vps::stf<TO>(y.p + y.off(n, Y, X) + k, v);
 }
 
+// bf16 fast path: one thread assembles 8 consecutive output channels (scalar, L1-resident reads of the four source
+// pixels) and writes them with one 16-byte store; the channel padding up to the pixel stride is written as zeros.
+__global__ void space_to_depth2_bf16x8_kernel(vps::TV<const __nv_bfloat16> x, vps::TV<__nv_bfloat16> y) {
+  const int chunks = y.cs / 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= y.w * chunks) return;
+  const int k0 = (t % chunks) * 8, X = t / chunks, Y = blockIdx.y, n = blockIdx.z;
+  const int C = x.c;
+  int c = k0 % C, q = k0 / C;
+  uint32_t pk[4];
+#pragma unroll
+  for (int j2 = 0; j2 < 4; ++j2) {
+    unsigned short v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int iy = 2 * Y + (q >> 1), ix = 2 * X + (q & 1);
+      v[e] = 0;
+      if (q < 4 && iy < x.h && ix < x.w) v[e] = *reinterpret_cast<const unsigned short*>(x.p + x.off(n, iy, ix) + c);
+      if (++c == C) { c = 0; ++q; }
+    }
+    pk[j2] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+  }
+  *reinterpret_cast<uint4*>(y.p + y.off(n, Y, X) + k0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 // ---- GroupNorm: pass 1 = per-(n,group) sum / sumsq in double via block partials; pass 2 = apply
 template <typename TI>
 __global__ void gn_stats_kernel(vps::TV<const TI> x, int groups, double* __restrict__ stats) {
@@ -502,6 +527,12 @@ extern "C" int vps_sigmoid_flat(const vps_tensor* t, float* dst, void* stream) {
 extern "C" int vps_space_to_depth2(const vps_tensor* x, const vps_tensor* y, void* stream) {
   VPS_CHECK_ARG(y->c == 4 * x->c && y->h == (x->h + 1) / 2 && y->w == (x->w + 1) / 2 && y->n == x->n, "space_to_depth2: shapes");
   if (!((int64_t)y->n * y->h * y->w * y->c)) return VPS_OK;
+  if (x->dtype == VPS_BF16 && y->dtype == VPS_BF16 && y->cs % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0 && y->cs >= y->c) {
+    space_to_depth2_bf16x8_kernel<<<vps::pix_grid(y->w, y->cs / 8, y->h, y->n), 256, 0, (cudaStream_t)stream>>>(
+        vps::tv<const __nv_bfloat16>(*x), vps::tv<__nv_bfloat16>(*y));
+    VPS_CUDA_LAST("space_to_depth2");
+    return VPS_OK;
+  }
   DISPATCH_IO(x->dtype, y->dtype, TI, TO,
               (space_to_depth2_kernel<TI, TO><<<vps::pix_grid(y->w, y->c, y->h, y->n), 256, 0, (cudaStream_t)stream>>>(
                   vps::tv<const TI>(*x), vps::tv<TO>(*y))));

@@ -70,6 +70,7 @@ class PanopticFuseTrack(nn.Module):
         self.flownet2 = FlowNet2(rgb_max=255.0)
         self.precision = precision
         self.use_cuda_graph = True
+        self.label_dtype = torch.int64        # dtype of the label maps: int64 as torch.max returns in the reference, or torch.uint8
         self._graphs = {}
         self.reset_tracker()
         self.eval()
@@ -290,8 +291,8 @@ class PanopticFuseTrack(nn.Module):
                              torch.empty(nthings, H, W, dtype=torch.uint8, device=dev), nthings,
                              torch.empty(2 * k, dtype=torch.int32, device=dev), torch.empty(k, dtype=torch.int32, device=dev),
                              keep_sorted, nkeep)
-        pano = torch.empty(H, W, dtype=torch.int64, device=dev)
-        sem = torch.empty(H, W, dtype=torch.int64, device=dev)
+        pano = torch.empty(H, W, dtype=self.label_dtype, device=dev)
+        sem = torch.empty(H, W, dtype=self.label_dtype, device=dev)
         num_stuff = self.panopticFPN.num_stuff_classes
         ops.panoptic_fuse(fcn_score, det_boxes_c, cls_idx, mask_logit, ms, keep_sorted, nkeep, MAX_DET_CAP, num_stuff,
                           dummy, H, W, pano, sem)

@@ -342,6 +342,8 @@ class UPSNetFPN(_Prepared):
             _DeformConvWithOffset(in_channels, out_channels), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True),
             _DeformConvWithOffset(out_channels, out_channels), nn.GroupNorm(32, out_channels), nn.ReLU(inplace=True))])
         self.conv_pred = _ConvModule(out_channels * 4, num_classes, 1)
+        # below this many pixels (< 1 tile per SM) the fused kernel is latency bound and im2col + GEMM is faster (measured)
+        self.fused_dcn_min_pixels = 128 * 256
 
     def _pack(self):
         seq = self.deform_convs[0]
@@ -352,7 +354,8 @@ class UPSNetFPN(_Prepared):
             co, ci = w.shape[:2]
             # columns are tap-major: k*C + c  (vps_deform_im2col) -> 1x1 conv weight [co, 9*ci]
             w1 = w.permute(0, 2, 3, 1).reshape(co, 9 * ci, 1, 1).contiguous()
-            self.k_dcn.append(dict(off=_conv(d.conv_offset), gemm=Conv(w1, None), gamma=gn.weight.detach().float().contiguous(),
+            self.k_dcn.append(dict(off=_conv(d.conv_offset), gemm=Conv(w1, None), pk3=ops.PackedConv(w, None),
+                                   gamma=gn.weight.detach().float().contiguous(),
                                    beta=gn.bias.detach().float().contiguous(), eps=gn.eps, groups=gn.num_groups))
         self.k_pred = _conv(self.conv_pred.conv)
 
@@ -360,9 +363,14 @@ class UPSNetFPN(_Prepared):
         n, h, w, _ = x.shape
         for j, L in enumerate(self.k_dcn):
             off = L['off'](x, out_dtype=torch.float32)
-            cols = empty_nhwc(n, h, w, 9 * x.shape[3], x.dtype, x.device)
-            ops.deform_im2col(x, off, cols)
-            y = L['gemm'](cols)
+            if x.dtype == torch.bfloat16 and x.shape[3] % 64 == 0 and L['pk3'].cout <= 256 and n * h * w >= self.fused_dcn_min_pixels:
+                # fused: sampled columns go straight into the tensor-core operand ring (no 9x column matrix in HBM)
+                y = empty_nhwc(n, h, w, L['pk3'].cout, x.dtype, x.device)
+                ops.deform_conv_tc(x, off, L['pk3'], y)
+            else:
+                cols = empty_nhwc(n, h, w, 9 * x.shape[3], x.dtype, x.device)
+                ops.deform_im2col(x, off, cols)
+                y = L['gemm'](cols)
             dst = out_last if (j == len(self.k_dcn) - 1 and out_last is not None) else y
             ops.groupnorm(y, dst, L['gamma'], L['beta'], L['groups'], L['eps'], relu=True)
             x = dst

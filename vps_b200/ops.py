@@ -296,6 +296,15 @@ def deform_im2col(x, offset, cols):
     return cols
 
 
+def deform_conv_tc(x, offset, pw, y):
+    """fused DCNv1 3x3: x bf16 NHWC, offset f32 NHWC [..,18], pw = PackedConv of the OIHW kernel, y NHWC [.., cout]"""
+    if PROFILE is not None:
+        _NOTE["flops"] = 2 * x.shape[0] * x.shape[1] * x.shape[2] * pw.cout * pw.cin * 9
+        _NOTE["tag"] = "dcn3x3 %d->%d @%dx%d" % (pw.cin, pw.cout, x.shape[1], x.shape[2])
+    check(lib().vps_deform_conv_tc(_bt(x), _bt(offset), C.c_void_p(pw.tc().data_ptr()), pw.cout, _bt(y), stream()), "deform_conv_tc")
+    return y
+
+
 # ------------------------------------------------------------------ detection
 def roi_align(feats, strides, rois, nroi, out, sample_num=2, nroi_dev=None):
     arr = (VpsTensor * len(feats))(*[vt(f) for f in feats])
@@ -377,7 +386,7 @@ def panoptic_fuse(fcn_score, boxes, cls_idx, mask_logit, msize, keep_sorted, nke
                   pano_out, sem_out):
     check(lib().vps_panoptic_fuse(_bt(fcn_score), _ptr(boxes), _ptr(cls_idx), _ptr(mask_logit), msize, _ptr(keep_sorted),
                                   _ptr(nkeep_dev), kcap, num_stuff, int(dummy), H, W, _ptr(pano_out), _ptr(sem_out),
-                                  stream()), "panoptic_fuse")
+                                  pano_out.element_size(), stream()), "panoptic_fuse")
 
 
 def rpn_finalize(dets_cat, counts, nlev, seg, cap, scores_ws, scores_sorted_ws, idx_sorted_ws, sort_ws, proposals, rois,
