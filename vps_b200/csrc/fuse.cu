@@ -100,7 +100,7 @@ __global__ void mr_apply_kernel(const float* __restrict__ boxes, const int32_t* 
 
 // ---- class-parallel MaskRemoval: boxes of different classes never interact (the occupancy image is per class,
 // mask_removal.py:44,81-85), so the sequential dependence only runs along each class's score-ordered chain.
-// Step t handles the t-th box of EVERY class at once; one cooperative launch, two grid syncs per step.
+// Boxes grouped by class in score order (MaskRemoval only compares boxes of the same class, mask_removal.py:40-58).
 struct MrSched { int slot[8][MAX_DET_K]; int count[8]; int steps; };
 
 __global__ void mr_schedule_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ cls_idx, int k,
@@ -118,50 +118,48 @@ __global__ void mr_schedule_kernel(const int32_t* __restrict__ order, const int3
   sc->steps = steps;
 }
 
-__global__ void __launch_bounds__(256) mr_coop_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ order,
-                                                      const float* __restrict__ mask_logit, int ms,
-                                                      const int32_t* __restrict__ cls_idx, int H, int W, float frac_thr,
-                                                      uint8_t* __restrict__ occ, unsigned int* __restrict__ counters,
-                                                      int32_t* __restrict__ keep_flag, const MrSched* __restrict__ sc) {
+// One 8-CTA thread-block cluster per thing class: the boxes of a class are handled in score order with two hardware
+// cluster barriers per box (count -> decide/apply); classes never wait for each other and no grid-wide sync exists.
+constexpr int MR_CLUSTER = 8;
+__global__ void __cluster_dims__(MR_CLUSTER, 1, 1) __launch_bounds__(256)
+mr_cluster_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ order, const float* __restrict__ mask_logit,
+                  int ms, const int32_t* __restrict__ cls_idx, int H, int W, float frac_thr, uint8_t* __restrict__ occ,
+                  unsigned int* __restrict__ counters, int32_t* __restrict__ keep_flag, const MrSched* __restrict__ sc) {
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  const int steps = sc->steps;
-  for (int t = 0; t < steps; ++t) {
-    int act[8], nact = 0;
-    for (int c = 0; c < 8; ++c)
-      if (sc->count[c] > t) act[nact++] = sc->slot[c][t];
-    const int mine = blockIdx.x % nact, part = blockIdx.x / nact;
-    const int nparts = ((int)gridDim.x - mine + nact - 1) / nact;
-    const int pos = act[mine];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cls = blockIdx.x / MR_CLUSTER;
+  const int part = (int)cluster.block_rank(), nparts = MR_CLUSTER;
+  const int cnt = sc->count[cls];
+  uint8_t* oc = occ + (int64_t)cls * H * W;
+  for (int t = 0; t < cnt; ++t) {
+    const int pos = sc->slot[cls][t];
     const int det = order[pos];
-    const int cls = cls_idx[det] - 1;
     const BoxI b = int_box(boxes + (int64_t)det * 4, H, W);
     const int cw = b.x_1 - b.x_0, ch = b.y_1 - b.y_0;
     const float* ml = mask_logit + (int64_t)det * ms * ms;
-    uint8_t* oc = occ + (int64_t)cls * H * W;
-    const int64_t total = (cw > 0 && ch > 0) ? (int64_t)cw * ch : 0;
-    // ---- count
+    const int total = (cw > 0 && ch > 0) ? cw * ch : 0;
+    // ---- count mask pixels and those already occupied by a kept box of this class
     unsigned int msum = 0, osum = 0;
-    for (int64_t i = (int64_t)part * blockDim.x + threadIdx.x; i < total; i += (int64_t)nparts * blockDim.x) {
-      const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
+    for (int i = part * blockDim.x + threadIdx.x; i < total; i += nparts * blockDim.x) {
+      const int x = b.x_0 + i % cw, y = b.y_0 + i / cw;
       const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
       if (v > 0.f) { msum++; if (__ldcg(oc + (int64_t)y * W + x) >= 1) osum++; }   // L2 reads: other SMs wrote it
     }
     for (int o = 16; o > 0; o >>= 1) { msum += __shfl_xor_sync(0xffffffffu, msum, o); osum += __shfl_xor_sync(0xffffffffu, osum, o); }
     if ((threadIdx.x & 31) == 0 && (msum | osum)) { atomicAdd(counters + 2 * pos, msum); atomicAdd(counters + 2 * pos + 1, osum); }
-    grid.sync();
+    cluster.sync();
     // ---- decide + apply
     const unsigned int ms_all = __ldcg(counters + 2 * pos), os_all = __ldcg(counters + 2 * pos + 1);
     const bool keep = ms_all != 0 && !((double)os_all / (double)ms_all > (double)frac_thr);
     if (part == 0 && threadIdx.x == 0) keep_flag[pos] = keep ? 1 : 0;
     if (keep) {
-      for (int64_t i = (int64_t)part * blockDim.x + threadIdx.x; i < total; i += (int64_t)nparts * blockDim.x) {
-        const int x = b.x_0 + (int)(i % cw), y = b.y_0 + (int)(i / cw);
+      for (int i = part * blockDim.x + threadIdx.x; i < total; i += nparts * blockDim.x) {
+        const int x = b.x_0 + i % cw, y = b.y_0 + i / cw;
         const float v = cv_resize_linear(ml, ms, b.w, b.h, y - b.y1, x - b.x1);
         if (v > 0.f) { uint8_t* q = oc + (int64_t)y * W + x; __stcg(q, (uint8_t)(__ldcg(q) + 1)); }
       }
     }
-    grid.sync();
+    cluster.sync();
   }
 }
 
@@ -206,24 +204,68 @@ __global__ void fuse_prepare_kernel(const float* __restrict__ boxes, const int32
   ip->px0[j] = r.x_0; ip->px1[j] = r.x_1; ip->py0[j] = r.y_0; ip->py1[j] = r.y_1;
 }
 
+// One block = one 32 x 8 pixel tile.  Instances whose SegTerm box and paste box both miss the tile contribute the
+// constant logit 0 there; only the FIRST of them can ever win the first-max argmax, so the tile's candidate list is
+// {instances overlapping the tile} + {first non-overlapping instance}, in instance order -- identical results to the
+// reference's dense [stuff | instances] argmax, without looping over every instance at every pixel.
+constexpr int FUSE_TW = 32, FUSE_TH = 8;
 template <typename T, typename TL>
-__global__ void __launch_bounds__(256) panoptic_fuse_kernel(vps::TV<const T> score, const float* __restrict__ mask_logit,
+__global__ void __launch_bounds__(FUSE_TW * FUSE_TH) panoptic_fuse_kernel(vps::TV<const T> score, const float* __restrict__ mask_logit,
                                                             int ms, const InstParams* __restrict__ ipg,
                                                             const int* __restrict__ ninst_dev, int num_stuff, int dummy,
                                                             int H, int W, TL* __restrict__ pano, TL* __restrict__ sem) {
-  __shared__ InstParams ip;
-  {
-    const int* src = (const int*)ipg;
-    int* dst = (int*)&ip;
-    for (int i = threadIdx.x; i < (int)(sizeof(InstParams) / 4); i += blockDim.x) dst[i] = src[i];
+  __shared__ int s_cnt[4], s_first[4];
+  __shared__ int s_j[MAX_INST], s_seg[MAX_INST], s_det[MAX_INST];
+  __shared__ int s_sy0[MAX_INST], s_sy1[MAX_INST], s_sx0[MAX_INST], s_sx1[MAX_INST];
+  __shared__ int s_py0[MAX_INST], s_py1[MAX_INST], s_px0[MAX_INST], s_px1[MAX_INST];
+  __shared__ int s_bx1[MAX_INST], s_by1[MAX_INST], s_bw[MAX_INST], s_bh[MAX_INST];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx0 = blockIdx.x * FUSE_TW, ty0 = blockIdx.y * FUSE_TH;
+  const int ninst = dummy ? 0 : *ninst_dev;
+  // ---- candidate list of this tile (threads 0..127 = instances)
+  bool hit = false, valid = false;
+  int rank_in_warp = 0;
+  int sy0 = 0, sy1 = 0, sx0 = 0, sx1 = 0, py0 = 0, py1 = 0, px0 = 0, px1 = 0, seg = -1;
+  if (tid < MAX_INST) {
+    valid = tid < ninst;
+    if (valid) {
+      sy0 = ipg->sy0[tid]; sy1 = ipg->sy1[tid]; sx0 = ipg->sx0[tid]; sx1 = ipg->sx1[tid];
+      py0 = ipg->py0[tid]; py1 = ipg->py1[tid]; px0 = ipg->px0[tid]; px1 = ipg->px1[tid];
+      seg = ipg->seg_ch[tid];
+      const bool hs = seg >= 0 && sy0 < ty0 + FUSE_TH && sy1 > ty0 && sx0 < tx0 + FUSE_TW && sx1 > tx0;
+      const bool hp = py0 < ty0 + FUSE_TH && py1 > ty0 && px0 < tx0 + FUSE_TW && px1 > tx0;
+      hit = hs || hp;
+    }
+    const unsigned miss = __ballot_sync(0xffffffffu, valid && !hit);
+    if (lane == 0) s_first[warp] = miss ? warp * 32 + (__ffs(miss) - 1) : 0x7fffffff;
   }
   __syncthreads();
-  const int ninst = *ninst_dev;
+  if (tid < MAX_INST) {
+    const int first_miss = min(min(s_first[0], s_first[1]), min(s_first[2], s_first[3]));
+    const bool listed = hit || tid == first_miss;
+    const unsigned bal = __ballot_sync(0xffffffffu, listed);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    rank_in_warp = __popc(bal & ((1u << lane) - 1u));
+    hit = listed;
+  }
+  __syncthreads();
+  if (tid < MAX_INST && hit) {
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_cnt[w];
+    const int slot = base + rank_in_warp;
+    s_j[slot] = tid; s_seg[slot] = seg; s_det[slot] = ipg->det[tid];
+    s_sy0[slot] = sy0; s_sy1[slot] = sy1; s_sx0[slot] = sx0; s_sx1[slot] = sx1;
+    s_py0[slot] = py0; s_py1[slot] = py1; s_px0[slot] = px0; s_px1[slot] = px1;
+    s_bx1[slot] = ipg->bx1[tid]; s_by1[slot] = ipg->by1[tid]; s_bw[slot] = ipg->bw[tid]; s_bh[slot] = ipg->bh[tid];
+  }
+  __syncthreads();
+  const int nlist = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+  const int X = tx0 + lane, Y = ty0 + warp;
+  if (X >= W || Y >= H) return;
   const int NC = score.c;
   const float sy = (float)score.h / (float)H, sx = (float)score.w / (float)W;
-  const int64_t total = (int64_t)H * W;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int X = (int)(i % W), Y = (int)(i / W);
+  const int64_t i = (int64_t)Y * W + X;
+  {
     // fcn_output = bilinear x4 (align_corners False) of fcn_score (upsnetFPN.py:59,80)
     const float fy = fmaxf(sy * ((float)Y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)X + 0.5f) - 0.5f, 0.f);
     const int y0 = (int)fy, x0 = (int)fx;
@@ -255,18 +297,18 @@ __global__ void __launch_bounds__(256) panoptic_fuse_kernel(vps::TV<const T> sco
       // MaskROI dummy detection (mask_roi.py:136-142): one all-zero instance channel
       if (0.f > bp) { bp = 0.f; bpi = num_stuff; }
     } else {
-      for (int j = 0; j < ninst; ++j) {
+      for (int q = 0; q < nlist; ++q) {
         float v = 0.f;
-        if (ip.seg_ch[j] >= 0 && Y >= ip.sy0[j] && Y < ip.sy1[j] && X >= ip.sx0[j] && X < ip.sx1[j]) {
-          float s = 0.f;
-          const int ch = ip.seg_ch[j];
+        const int ch = s_seg[q];
+        if (ch >= 0 && Y >= s_sy0[q] && Y < s_sy1[q] && X >= s_sx0[q] && X < s_sx1[q]) {
+          float sv = 0.f;
 #pragma unroll
-          for (int c = 0; c < 24; ++c) if (c == ch) s = fo[c];
-          v = s;
+          for (int c = 0; c < 24; ++c) if (c == ch) sv = fo[c];
+          v = sv;
         }
-        if (Y >= ip.py0[j] && Y < ip.py1[j] && X >= ip.px0[j] && X < ip.px1[j])
-          v += cv_resize_linear(mask_logit + (int64_t)ip.det[j] * ms * ms, ms, ip.bw[j], ip.bh[j], Y - ip.by1[j], X - ip.bx1[j]);
-        if (v > bp) { bp = v; bpi = num_stuff + j; }
+        if (Y >= s_py0[q] && Y < s_py1[q] && X >= s_px0[q] && X < s_px1[q])
+          v += cv_resize_linear(mask_logit + (int64_t)s_det[q] * ms * ms, ms, s_bw[q], s_bh[q], Y - s_by1[q], X - s_bx1[q]);
+        if (v > bp) { bp = v; bpi = num_stuff + s_j[q]; }
       }
     }
     pano[i] = (TL)bpi;
@@ -287,23 +329,12 @@ extern "C" int vps_mask_removal(const float* boxes, const int32_t* order, int k,
   cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 2 * k, st);
   cudaMemsetAsync(keep_flag, 0, sizeof(int32_t) * k, st);
   static MrSched* d_sched = nullptr;
-  static int coop_ok = -1, coop_grid = 0;
-  if (coop_ok < 0) {
-    int dev = 0, sup = 0, nsm = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sup, cudaDevAttrCooperativeLaunch, dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mr_coop_kernel, 256, 0);
-    coop_ok = (sup && per_sm >= 1 && k <= MAX_DET_K && cudaMalloc(&d_sched, sizeof(MrSched)) == cudaSuccess) ? 1 : 0;
-    coop_grid = nsm;
-  }
-  if (coop_ok == 1 && k <= MAX_DET_K && num_things <= 8) {
+  if (!d_sched && cudaMalloc(&d_sched, sizeof(MrSched)) != cudaSuccess) { vps::set_error("mask_removal: malloc"); return VPS_E_CUDA; }
+  if (k <= MAX_DET_K && num_things <= 8) {
     mr_schedule_kernel<<<1, 32, 0, st>>>(order, cls_idx, k, k_dev, num_things, d_sched);
-    void* args[] = {(void*)&boxes, (void*)&order, (void*)&mask_logit, (void*)&msize, (void*)&cls_idx, (void*)&H, (void*)&W,
-                    (void*)&frac_thr, (void*)&occ, (void*)&counters, (void*)&keep_flag, (void*)&d_sched};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)mr_coop_kernel, dim3(coop_grid), dim3(256), args, 0, st);
-    if (e != cudaSuccess) { vps::set_error("mask_removal: cooperative launch: %s", cudaGetErrorString(e)); return VPS_E_CUDA; }
-    vps::count_launch(2);
+    mr_cluster_kernel<<<num_things * MR_CLUSTER, 256, 0, st>>>(boxes, order, mask_logit, msize, cls_idx, H, W, frac_thr, occ,
+                                                               counters, keep_flag, d_sched);
+    vps::count_launch(1);
   } else {
     for (int pos = 0; pos < k; ++pos) {
       mr_count_kernel<<<148, 256, 0, st>>>(boxes, order, pos, k, k_dev, mask_logit, msize, cls_idx, H, W, occ, counters);
@@ -336,12 +367,13 @@ extern "C" int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes
     fuse_prepare_kernel<<<1, MAX_INST, 0, st>>>(boxes, cls_idx, keep_sorted, nkeep_dev, kcap, num_stuff, H, W, g_ip, g_ninst);
     VPS_CUDA_LAST("fuse_prepare");
   }
+  const dim3 fgrid((unsigned)vps::cdiv(W, FUSE_TW), (unsigned)vps::cdiv(H, FUSE_TH));
   if (label_bytes == 8) {
-    VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T, int64_t><<<148 * 4, 256, 0, st>>>(
+    VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T, int64_t><<<fgrid, FUSE_TW * FUSE_TH, 0, st>>>(
                                             vps::tv<const T>(*fcn_score), mask_logit, msize, g_ip, g_ninst, num_stuff, dummy,
                                             H, W, (int64_t*)pano_out, (int64_t*)sem_out)));
   } else {
-    VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T, uint8_t><<<148 * 4, 256, 0, st>>>(
+    VPS_DISPATCH_T(fcn_score->dtype, T, (panoptic_fuse_kernel<T, uint8_t><<<fgrid, FUSE_TW * FUSE_TH, 0, st>>>(
                                             vps::tv<const T>(*fcn_score), mask_logit, msize, g_ip, g_ninst, num_stuff, dummy,
                                             H, W, (uint8_t*)pano_out, (uint8_t*)sem_out)));
   }
