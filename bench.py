@@ -307,11 +307,29 @@ def run_gpu_arm(args):
             line["breakdown"] = breakdown
             line["stages"] = {k: {"ms": round(v[0], 3), "gflop": round(v[1] / 1e9, 1)} for k, v in scopes.items()}
             if "r50fpn" in scopes:      # north-star target: fraction of the conv-FLOP roofline on 2 x ResNet-50-FPN
-                t = scopes["r50fpn"][0] * 1e-3
+                # the stage alone (both frames, batch of 2), captured as its own CUDA graph and replayed between L2
+                # flushes: the kernels run back to back exactly as inside the step's graph
+                from vps_b200.layers import empty_nhwc
+                xr = empty_nhwc(2, H, W, 3, det.act_dtype, dev)
+                xr.normal_()
+                det.extract_feat(xr)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    det.extract_feat(xr)
+                reps = []
+                for i in range(5):
+                    flush.fill_(i)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); g.replay(); b.record()
+                    reps.append((a, b))
+                torch.cuda.synchronize()
+                r50_ms = sorted(a.elapsed_time(b) for a, b in reps)[len(reps) // 2]
+                t = r50_ms * 1e-3
                 ach = GFLOP_R50FPN_PAIR * (H * W) / float(H_FULL * W_FULL) * 1e9 / t / 1e12
                 line["r50fpn_roofline"] = {"achieved": ach, "peak": peaks()["tf_sus"], "unit": "TFLOP/s",
-                                           "frac": ach / peaks()["tf_sus"], "ms": scopes["r50fpn"][0],
-                                           "note": "eager instrumented step (CUDA events per call), algorithmic 1158.4 GFLOP/pair"}
+                                           "frac": ach / peaks()["tf_sus"], "ms": r50_ms, "eager_instrumented_ms": scopes["r50fpn"][0],
+                                           "note": "stage captured as its own CUDA graph, median of 5 replays with L2 flush; algorithmic 1158.4 GFLOP/pair"}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

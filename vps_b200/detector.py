@@ -186,12 +186,15 @@ class PanopticFuseTrack(nn.Module):
         ops.SCOPE[0] = 'flownet2'
         flow = self.compute_flow(img, ref_img, 0.25, taps)
         ops.SCOPE[0] = 'r50fpn'
-        x_in = empty_nhwc(1, H, W, 3, dt, dev)
-        r_in = empty_nhwc(1, H, W, 3, dt, dev)
-        ops.nchw_to_nhwc(img, x_in)
-        ops.nchw_to_nhwc(ref_img, r_in)
-        x = self.extract_feat(x_in)
-        ref_x = self.extract_feat(r_in)
+        # both frames go through ResNet-50-FPN as ONE batch of 2 (the reference runs extract_feat twice,
+        # panoptic_fusetrack.py:516-517; frozen BN makes the batched pass identical per image): half the launches, twice
+        # the tiles per launch for the small-spatial stages, weights fetched once
+        xr_in = empty_nhwc(2, H, W, 3, dt, dev)
+        ops.nchw_to_nhwc(img, xr_in[0:1])
+        ops.nchw_to_nhwc(ref_img, xr_in[1:2])
+        feats = self.extract_feat(xr_in)
+        x = tuple(f[0:1] for f in feats)
+        ref_x = tuple(f[1:2] for f in feats)
         ops.SCOPE[0] = 'bfp_tcea'
         xf = self.extra_neck(x, ref_x, flow, taps)
         ops.SCOPE[0] = 'upsnet_fpn'
