@@ -142,3 +142,41 @@ def test_stem_7x7s2_space_to_depth(cuda, cin, h, w):
     assert got.shape == ref.shape
     err = (got - ref).abs().max().item()
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), "max err %g" % err
+
+
+BF16_OUT_CASES = [
+    # n, cin, cout, h, w, k, stride, pad, with_residual
+    (1, 64, 256, 37, 53, 1, 1, 0, True),      # bottleneck expand + residual, ragged tiles
+    (2, 128, 128, 24, 40, 3, 1, 1, False),    # halo mode, N = 128
+    (1, 96, 64, 33, 20, 3, 2, 1, False),      # flat stride 2, N = 64
+    (1, 256, 320, 16, 24, 1, 1, 0, True),     # several N tiles
+    (1, 64, 48, 16, 16, 3, 1, 1, False),      # partial 32-column chunk (16-byte store groups)
+]
+
+
+@pytest.mark.parametrize("case", BF16_OUT_CASES)
+def test_conv_tc_bf16_output_epilogues(cuda, case):
+    """bf16 outputs (the production dtype) with bias, ReLU and a residual added before the activation
+    (resnet.py:236-258), written into a channel slice of a wider buffer whose other channels must stay untouched."""
+    from vps_b200 import ops
+    n, cin, cout, h, w, k, s, p, with_res = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xq, wq = x.bfloat16().float(), wt.bfloat16().float()
+    pre = F.conv2d(xq, wq, b, stride=s, padding=p)
+    oh, ow = pre.shape[2:]
+    res = torch.randn(n, cout, oh, ow, generator=g).bfloat16().float() if with_res else None
+    ref = F.relu(pre + res) if with_res else F.relu(pre)
+    pk = ops.PackedConv(wt.to(cuda), b.to(cuda))
+    xd = _nhwc(x, torch.bfloat16).to(cuda)[..., :cin]
+    wide = torch.full((n, oh, ow, cout + 32), 7.0, dtype=torch.bfloat16, device=cuda)     # slice [16, 16 + cout)
+    y = wide[..., 16:16 + cout]
+    rd = _nhwc(res, torch.bfloat16).to(cuda)[..., :cout] if with_res else None
+    ops.conv2d(xd, pk, y, stride=s, pad=p, act=ops.ACT_RELU, res=rd)
+    torch.cuda.synchronize()
+    got = y.float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item()
+    assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), "max err %g" % err
+    assert float((wide[..., :16].float() - 7.0).abs().max()) == 0.0 and float((wide[..., 16 + cout:].float() - 7.0).abs().max()) == 0.0
