@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256) gn_stats_vec_kernel(vps::TV<const TI> x, 
   }
 }
 
+constexpr int GN_MAX_C = 1024;
 // mean / rstd of every (n, group) are finalised ONCE per block into shared memory (fp64 divides per element made this
 // kernel ALU-bound); the per-element expression (v - mean) * rstd * gamma + beta is unchanged.
 template <typename TI, typename TO, int V>
@@ -244,7 +245,9 @@ __global__ void gn_apply_kernel(vps::TV<const TI> x, vps::TV<TO> y, const double
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                                 int relu) {
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_gamma[GN_MAX_C], s_beta[GN_MAX_C];      // per-element global loads of gamma/beta made this LSU-bound
   const int cg = x.c / groups;
+  for (int c = threadIdx.x; c < x.c; c += blockDim.x) { s_gamma[c] = gamma[c]; s_beta[c] = beta[c]; }
   {
     const int n_blk = blockIdx.z;                    // pix_grid: z = image index
     const double cnt = (double)x.h * x.w * cg;
@@ -263,7 +266,7 @@ __global__ void gn_apply_kernel(vps::TV<const TI> x, vps::TV<TO> y, const double
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const int g = (V > 1 && cg < V) ? g0 + (j >= cg ? 1 : 0) : (cg % V == 0 ? g0 : (c + j) / cg);
-    float o = (v[j] - s_mean[g]) * s_rstd[g] * gamma[c + j] + beta[c + j];
+    float o = (v[j] - s_mean[g]) * s_rstd[g] * s_gamma[c + j] + s_beta[c + j];
     v[j] = relu ? fmaxf(o, 0.f) : o;
   }
   vps::stv<TO, V>(y.p + y.off(n, yy, xx) + c, v);
@@ -443,7 +446,7 @@ namespace { double* g_gn_stats = nullptr; int64_t g_gn_cap = 0; }
 extern "C" int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const float* gamma, const float* beta,
                              int groups, float eps, int relu, void* stream) {
   VPS_CHECK_ARG(x->c % groups == 0 && x->c == y->c && x->h == y->h && x->w == y->w, "groupnorm: shape");
-  VPS_CHECK_ARG(groups >= 1 && groups <= 64, "groupnorm: groups %d not in [1, 64]", groups);
+  VPS_CHECK_ARG(groups >= 1 && groups <= 64 && x->c <= GN_MAX_C, "groupnorm: groups %d not in [1, 64] or c %d > %d", groups, x->c, GN_MAX_C);
   const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
   if (!total) return VPS_OK;
   cudaStream_t st = (cudaStream_t)stream;
