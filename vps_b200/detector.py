@@ -183,9 +183,14 @@ class PanopticFuseTrack(nn.Module):
         dev = img.device
         _, _, H, W = img.shape
         dt = self.act_dtype
-        ops.SCOPE[0] = 'flownet2'
-        flow = self.compute_flow(img, ref_img, 0.25, taps)
+        # ResNet-50-FPN does not depend on the flow: it runs as a parallel branch (side stream / parallel graph branch), so
+        # the many launches that cannot fill 148 SMs on either side overlap with the other side's kernels
+        br = ops.Branch("r50fpn")
+        if br.side is None:
+            ops.SCOPE[0] = 'flownet2'
+            flow = self.compute_flow(img, ref_img, 0.25, taps)
         ops.SCOPE[0] = 'r50fpn'
+        br.__enter__()
         # both frames go through ResNet-50-FPN as ONE batch of 2 (the reference runs extract_feat twice,
         # panoptic_fusetrack.py:516-517; frozen BN makes the batched pass identical per image): half the launches, twice
         # the tiles per launch for the small-spatial stages, weights fetched once
@@ -193,13 +198,21 @@ class PanopticFuseTrack(nn.Module):
         ops.nchw_to_nhwc(img, xr_in[0:1])
         ops.nchw_to_nhwc(ref_img, xr_in[1:2])
         feats = self.extract_feat(xr_in)
+        br.__exit__(None, None, None)
+        if br.side is not None:
+            ops.SCOPE[0] = 'flownet2'
+            flow = self.compute_flow(img, ref_img, 0.25, taps)
+            br.join(*feats)
         x = tuple(f[0:1] for f in feats)
         ref_x = tuple(f[1:2] for f in feats)
         ops.SCOPE[0] = 'bfp_tcea'
         xf = self.extra_neck(x, ref_x, flow, taps)
         ops.SCOPE[0] = 'upsnet_fpn'
         nl = self.panopticFPN.num_levels
-        fcn_output, fcn_score = self.panopticFPN(xf[0:nl], want_full=taps is not None)
+        # the semantic head and the RPN -> bbox head -> MaskROI chain both start from xf and meet only in the fusion tail
+        br2 = ops.Branch("upsnet_fpn")
+        with br2:
+            fcn_output, fcn_score = self.panopticFPN(xf[0:nl], want_full=taps is not None)
         ops.SCOPE[0] = 'rpn'
         # RPN (test_mixins.py:13-17, rpn_head.py:55-104)
         heads = self.rpn_head(xf)
@@ -210,6 +223,7 @@ class PanopticFuseTrack(nn.Module):
         roi_feats = self.bbox_roi_extractor(xf, rois, nroi, nprop)
         cls_score, bbox_pred, _ = self.bbox_head(roi_feats)
         det_rois, cls_idx, cls_prob, kout = self._mask_roi(rois, cls_score, bbox_pred, nroi, nprop, float(H), float(W))
+        br2.join(fcn_score, fcn_output)
         return dict(flow=flow, x=x, ref_x=ref_x, xf=xf, fcn_output=fcn_output, fcn_score=fcn_score, heads=heads,
                     proposals=proposals_t, rois=rois, nprop=nprop, roi_feats=roi_feats, cls_score=cls_score,
                     bbox_pred=bbox_pred, det_rois=det_rois, cls_idx=cls_idx, cls_prob=cls_prob, kout=kout)

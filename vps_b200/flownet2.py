@@ -237,12 +237,16 @@ class FlowNet2(_Prepared):
             ops.channelnorm(img0, cat[..., 11:12], b=cat[..., 6:9])
             return cat
 
+        # FlowNetSD only reads x6: parallel branch next to the FlowNetC -> S1 -> S2 chain
+        br = ops.Branch("flownet_sd")
+        with br:
+            sd_flow2 = self.flownets_d(x6)
         c_flow2 = self.flownetc(x6)
         cat1 = stage(c_flow2)
         s1_flow2 = self.flownets_1(cat1)
         cat2 = stage(s1_flow2)
         s2_flow2 = self.flownets_2(cat2)
-        sd_flow2 = self.flownets_d(x6)
+        br.join(sd_flow2)
 
         # concat3 = (img0, sd_flow, s2_flow, |sd_flow|, |s2_flow|, |img0 - warp_sd|, |img0 - warp_s2|) flownet2.py:189
         cat3 = empty_nhwc(n, H, W, 11, dt, dev)

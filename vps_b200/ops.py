@@ -6,6 +6,7 @@ Tensors handed to these functions are torch CUDA tensors used purely as device-m
 valid view (pixel stride = buf.shape[-1]).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -48,6 +49,48 @@ def lib():  # noqa: F811  (shadows the import: every wrapper below goes through 
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Branch:
+    """Run an independent part of the frame-pair graph on a side stream (fork at __enter__, `join()` makes the current
+    stream wait for it).  Inside a CUDA-graph capture this records parallel branches, so kernels whose grids do not fill
+    the GPU (coarse pyramid levels, tails) overlap with the other branch.  VPS_BRANCHES=0 runs everything in line."""
+    _streams = {}
+    enabled = os.environ.get("VPS_BRANCHES", "1") != "0"
+
+    def __init__(self, name):
+        self.name = name
+        self.main = torch.cuda.current_stream()
+        if Branch.enabled and PROFILE is None:
+            key = (name, self.main.device.index)
+            if key not in Branch._streams:
+                Branch._streams[key] = torch.cuda.Stream(self.main.device)
+            self.side = Branch._streams[key]
+        else:
+            self.side = None
+        self._ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._ctx = None
+        return False
+
+    def join(self, *tensors):
+        """the current stream waits for the branch; `tensors` produced on the branch are marked as used by it"""
+        if self.side is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self.side)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(cur)
 
 
 def vt(t):
