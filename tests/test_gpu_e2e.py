@@ -135,7 +135,7 @@ def test_clip_runner_equals_direct_calls(models):
     _, prod = models
     prod.precision = "fp32"
     H, W = 128, 256
-    frames = [make_pair(H, W, seed=s) for s in (5, 6, 7, 8, 9)]
+    frames = [make_pair(H, W, seed=s) for s in (5, 6, 7, 8, 9, 10, 11, 12)]
     metas = [meta(10001 + f, H, W) for f in range(len(frames))]
     prod.label_dtype = torch.int64
     prod.reset_tracker()

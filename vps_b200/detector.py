@@ -72,6 +72,7 @@ class PanopticFuseTrack(nn.Module):
         self.use_cuda_graph = True
         self.label_dtype = torch.int64        # dtype of the label maps: int64 as torch.max returns in the reference, or torch.uint8
         self._graphs = {}
+        self._pf_stream, self._pf_queue, self._pf_next, self._tail_done = None, [], 0, [None, None]
         self.reset_tracker()
         self.eval()
 
@@ -228,10 +229,10 @@ class PanopticFuseTrack(nn.Module):
                     proposals=proposals_t, rois=rois, nprop=nprop, roi_feats=roi_feats, cls_score=cls_score,
                     bbox_pred=bbox_pred, det_rois=det_rois, cls_idx=cls_idx, cls_prob=cls_prob, kout=kout)
 
-    def _static_part(self, img, ref_img, img_shape, use_graph, taps=None):
+    def _static_part(self, img, ref_img, img_shape, use_graph, taps=None, slot=0):
         if not use_graph:
             return self._static_eager(img, ref_img, img_shape, taps)
-        key = (tuple(img.shape), img_shape, self.precision, img.device.index)
+        key = (tuple(img.shape), img_shape, self.precision, img.device.index, slot)   # slot: ping-pong graph instance
         ent = self._graphs.get(key)
         if ent is None:
             # first call for this key runs eagerly (lazy weight packing, function attributes, scratch allocations
@@ -255,6 +256,37 @@ class PanopticFuseTrack(nn.Module):
         ops.lib().vps_add_launch_count(nlaunch)            # kernels of ours re-launched by the replay
         return outs
 
+    @torch.no_grad()
+    def prefetch(self, img, img_meta, ref_img=None):
+        """Enqueue the static part (flow, backbones, necks, semantic head, RPN, bbox head, MaskROI -- everything that does
+        not depend on the tracker) of a FUTURE `simple_test(img, ...)` call on a side stream.  Two graph instances
+        ping-pong, so frame i+1's static part overlaps frame i's data-dependent tail and its host round-trips.  The
+        matching simple_test call (same `img` object, in call order) picks the result up; results are identical."""
+        if isinstance(ref_img, (list, tuple)):
+            ref_img = ref_img[0]
+        meta = img_meta[0] if isinstance(img_meta, (list, tuple)) else img_meta
+        if not (self.use_cuda_graph and ops.PROFILE is None):
+            return
+        self.prepare()
+        cur = torch.cuda.current_stream(img.device)
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(img.device)
+        st = self._pf_stream
+        slot = self._pf_next
+        self._pf_next ^= 1
+        st.wait_stream(cur)                                     # inputs are ready on the caller's stream
+        if self._tail_done[slot] is not None:
+            st.wait_event(self._tail_done[slot])                # the tail that last read this slot's outputs is done
+        with torch.cuda.stream(st):
+            a = img.contiguous().float()
+            b = ref_img.contiguous().float()
+            outs = self._static_part(a, b, tuple(meta['img_shape'][:2]), True, None, slot)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        img.record_stream(st)
+        ref_img.record_stream(st)
+        self._pf_queue.append((img, slot, outs, ev))
+
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
     def simple_test(self, img, img_meta, proposals=None, rescale=False, ref_img=None, taps=None):
@@ -269,12 +301,24 @@ class PanopticFuseTrack(nn.Module):
         dev = img.device
         n, _, H, W = img.shape
         assert n == 1
+        img_arg = img
         img = img.contiguous().float()
         ref_img = ref_img.contiguous().float()
         # ---- static part (flow, backbones, fuse neck, semantic head, RPN, bbox head, MaskROI): fixed shapes, no host
         # decisions -> replayed as ONE CUDA graph after the first eager call for this (shape, precision)
         use_graph = self.use_cuda_graph and taps is None and ops.PROFILE is None
-        st = self._static_part(img, ref_img, tuple(meta['img_shape'][:2]), use_graph, taps)
+        pf_slot = None
+        if self._pf_queue and self._pf_queue[0][0] is img_arg and taps is None:
+            _, pf_slot, st, ev = self._pf_queue.pop(0)           # static part was enqueued by prefetch()
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            for v in st.values():
+                for t in (v if isinstance(v, (tuple, list)) else (v,)):
+                    if torch.is_tensor(t):
+                        t.record_stream(cur)
+        else:
+            assert not self._pf_queue, "prefetch() / simple_test() calls out of order"
+            st = self._static_part(img, ref_img, tuple(meta['img_shape'][:2]), use_graph, taps)
         flow, x, ref_x, xf, fcn_output, fcn_score = st['flow'], st['x'], st['ref_x'], st['xf'], st['fcn_output'], st['fcn_score']
         heads, proposals_t, rois, nprop = st['heads'], st['proposals'], st['rois'], st['nprop']
         roi_feats, cls_score, bbox_pred = st['roi_feats'], st['cls_score'], st['bbox_pred']
@@ -340,6 +384,10 @@ class PanopticFuseTrack(nn.Module):
                         bbox_pred=bbox_pred, det_rois=det_rois[:k], cls_idx=cls_idx[:k], cls_prob=cls_prob[:k],
                         det_roi_feats=det_roi_feats, mask_logit=mask_logit, keep_inds=keep_h, det_obj_ids_all=ids_h,
                         order=order)
+        if pf_slot is not None:                                   # this slot's graph may be replayed once the tail is done
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            self._tail_done[pf_slot] = done
         return bbox_results, segm_results, pano_results
 
     # reference-compatible entry (base.py:79-104)

@@ -7,6 +7,10 @@ around the model call made asynchronous:
   * the label maps of the finished pair are downloaded into pinned buffers on the same copy stream, so the next
     pair's kernels do not wait for the D2H.
 
+  * the tracker-independent static part of the NEXT pair (`det.prefetch`: one CUDA-graph replay on a side stream, two
+    graph instances ping-pong) is enqueued before the current pair's data-dependent tail, so the tail and its host
+    round-trips overlap the next pair's graph.
+
 Nothing about the model call changes: `det.simple_test` is the same entry the parity tests use."""
 import torch
 
@@ -40,25 +44,40 @@ class ClipRunner:
             self._out[i % self.depth] = buf
         return buf
 
-    def run(self, pairs, metas):
-        """pairs: iterable of (img, ref_img) pinned host tensors [1,3,H,W] fp32; metas: matching img_meta dicts.
-        Yields (bbox_results, segm_results, pano_results) per pair, in order; pano_results['panoptic_outputs'] and
-        ['fcn_outputs'] are HOST tensors (pinned ring buffers, valid until `depth` further results were produced)."""
+    def _stage(self, pair, resident):
+        """make the pair available on the device: (img, ref, event or None)"""
+        if resident:
+            return pair[0], pair[1], None
+        return self._upload(pair)
+
+    def run(self, pairs, metas, resident=False, prefetch=True):
+        """pairs: iterable of (img, ref_img) pinned host tensors [1,3,H,W] fp32 (device tensors if `resident`); metas:
+        matching img_meta dicts.  Yields (bbox_results, segm_results, pano_results) per pair, in order;
+        pano_results['panoptic_outputs'] and ['fcn_outputs'] are HOST tensors (pinned ring buffers, valid until `depth`
+        further results were produced).  With `prefetch` the tracker-independent static part of pair i+1
+        (`det.prefetch`) is enqueued before pair i's data-dependent tail runs, so the two overlap."""
         main = torch.cuda.current_stream(self.dev)
         it = iter(zip(pairs, metas))
         cur = next(it, None)
         if cur is None:
             return
-        nxt_up = self._upload(cur[0])
+        staged = self._stage(cur[0], resident)
+        if staged[2] is not None:
+            main.wait_event(staged[2])
+        if prefetch:
+            self.det.prefetch(staged[0], [cur[1]], ref_img=[staged[1]])
         pending = None
         i = 0
         while cur is not None:
-            a, b, ev = nxt_up
+            a, b, _ = staged
             meta = cur[1]
-            main.wait_event(ev)
             cur = next(it, None)
             if cur is not None:
-                nxt_up = self._upload(cur[0])          # overlaps the compute below
+                staged = self._stage(cur[0], resident)          # upload overlaps the compute already in flight
+                if staged[2] is not None:
+                    main.wait_event(staged[2])
+                if prefetch:
+                    self.det.prefetch(staged[0], [cur[1]], ref_img=[staged[1]])
             r = self.det.simple_test(a, [meta], ref_img=[b])
             pano, sem = r[2]["panoptic_outputs"], r[2]["fcn_outputs"]
             done = torch.cuda.Event()
