@@ -248,6 +248,16 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     P.barrier()
     ms_e2e = [region(args.steps, args.warmup + 5 + args.steps, False)]
+    # host link check: the e2e region needs 50 MB of H2D per pair; a slow link (NUMA-remote pinned memory, shared PCIe)
+    # bounds e2e below `value` and shows up here
+    hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hs.record()
+    for i in range(4):
+        host[i % NPAIR][0].to(dev, non_blocking=True)
+        host[i % NPAIR][1].to(dev, non_blocking=True)
+    he.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 8 * 3 * H * W * 4 / (hs.elapsed_time(he) * 1e-3) / 1e9
     sampler.stop_flag = True
     seq_ms = timed(min(args.steps, 5), args.warmup)               # one pair at a time, L2 flushed: latency of a pair
     t_dev, t_e2e = [v / 1e3 for v in P.max_over_ranks([sum(ms), sum(ms_e2e)], dev)]     # max over ranks
@@ -302,7 +312,8 @@ def run_gpu_arm(args):
                                          "tracker/mask/fusion tail; max(W,5) + 2 untimed runner steps precede the timed regions",
                            "labels": "uint8 label maps (same values as the reference's int64; its collector casts to uint8)",
                            "precision_note": "bf16 operands / fp32 accumulate on tcgen05; fp32 parity mode via --precision fp32"},
-                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+                        "h2d_gbps_measured": round(h2d_gbps, 2)},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "sequential_ms_per_pair": float(np.median(seq_ms)),
                 "conv_flop_frac_whole_path": GFLOP_ALL_PAIR * (H * W) / float(H_FULL * W_FULL) * 1e9 * args.steps / t_dev / 1e12 / peaks()["tf_sus"]}

@@ -441,7 +441,8 @@ extern "C" int vps_pool2d(const vps_tensor* src, const vps_tensor* out, int k, i
   return VPS_OK;
 }
 
-namespace { double* g_gn_stats = nullptr; int64_t g_gn_cap = 0; }
+// statistics scratch: a ring of slots, one per call, so GroupNorm calls on parallel streams / graph branches never share one
+namespace { double* g_gn_ring = nullptr; unsigned g_gn_next = 0; constexpr int GN_SLOTS = 16; constexpr int GN_SLOT_DOUBLES = 4096; }
 
 extern "C" int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const float* gamma, const float* beta,
                              int groups, float eps, int relu, void* stream) {
@@ -451,11 +452,12 @@ extern "C" int vps_groupnorm(const vps_tensor* x, const vps_tensor* y, const flo
   if (!total) return VPS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t need = (int64_t)x->n * groups * 2;
-  if (g_gn_cap < need) {
-    if (g_gn_stats) cudaFree(g_gn_stats);
-    if (cudaMalloc(&g_gn_stats, need * sizeof(double) * 4) != cudaSuccess) { vps::set_error("groupnorm: malloc"); return VPS_E_CUDA; }
-    g_gn_cap = need * 4;
+  VPS_CHECK_ARG(need <= GN_SLOT_DOUBLES, "groupnorm: n * groups too large (%lld)", (long long)need);
+  if (!g_gn_ring && cudaMalloc(&g_gn_ring, sizeof(double) * GN_SLOTS * GN_SLOT_DOUBLES) != cudaSuccess) {
+    vps::set_error("groupnorm: malloc");
+    return VPS_E_CUDA;
   }
+  double* g_gn_stats = g_gn_ring + (size_t)(g_gn_next++ % GN_SLOTS) * GN_SLOT_DOUBLES;
   cudaMemsetAsync(g_gn_stats, 0, need * sizeof(double), st);
   const int64_t per_group = (int64_t)x->h * x->w * (x->c / groups);
   int chunks = (int)((per_group + 256 * 32 - 1) / (256 * 32));

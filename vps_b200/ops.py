@@ -56,13 +56,13 @@ class Branch:
     stream wait for it).  Inside a CUDA-graph capture this records parallel branches, so kernels whose grids do not fill
     the GPU (coarse pyramid levels, tails) overlap with the other branch.  VPS_BRANCHES=0 runs everything in line."""
     _streams = {}
-    enabled = os.environ.get("VPS_BRANCHES", "1") != "0"
+    max_level = int(os.environ.get("VPS_BRANCHES", "1"))     # 0: everything in line, 1: whole sub-networks as branches
 
-    def __init__(self, name):
+    def __init__(self, name, level=1):
         self.name = name
         self.main = torch.cuda.current_stream()
-        if Branch.enabled and PROFILE is None:
-            key = (name, self.main.device.index)
+        if level <= Branch.max_level and PROFILE is None:
+            key = (name, self.main.device.index, self.main.cuda_stream)     # one side stream per (branch, parent stream)
             if key not in Branch._streams:
                 Branch._streams[key] = torch.cuda.Stream(self.main.device)
             self.side = Branch._streams[key]
@@ -151,6 +151,7 @@ class PackedConv:
             buf = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=self.weight.device)
             check(lib().vps_pack_weights_tc(_ptr(self.weight), _ptr(self.scale), _ptr(buf), self.cout, self.cin,
                                             self.kh, self.kw, int(self.transposed), gran, stream()), "pack_weights_tc")
+            torch.cuda.current_stream().synchronize()   # one-time: the packed buffer may next be read from ANY stream / branch
             self._tc[gran] = buf
         return self._tc[gran]
 
@@ -161,6 +162,7 @@ class PackedConv:
             check(lib().vps_pack_weights_simt(_ptr(self.weight), _ptr(self.scale), _ptr(buf), self.cout, self.cin,
                                               self.kh, self.kw, int(self.transposed), stream()),
                   "pack_weights_simt")
+            torch.cuda.current_stream().synchronize()   # one-time: see tc()
             self._simt = buf
         return self._simt
 
