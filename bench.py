@@ -260,6 +260,23 @@ def run_gpu_arm(args):
     h2d_gbps = 8 * 3 * H * W * 4 / (hs.elapsed_time(he) * 1e-3) / 1e9
     sampler.stop_flag = True
     seq_ms = timed(min(args.steps, 5), args.warmup)               # one pair at a time, L2 flushed: latency of a pair
+    # ---- SURVEY 8f rank 1 (the step after the path): get_unified_pan_result on the GPU, timed alone on a real result
+    from vps_b200.postproc import PanUnifier
+    unifier = PanUnifier()
+    r_last = step(args.warmup)
+    u_args = (r_last[2]["fcn_outputs"], r_last[2]["panoptic_outputs"], r_last[2]["host"]["panoptic_cls_inds"],
+              r_last[2]["host"]["panoptic_det_obj_ids"])
+    unifier(*u_args)
+    torch.cuda.synchronize()
+    u_evs = []
+    for i in range(10):
+        flush.fill_(i)
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(); unifier(*u_args); b_.record()
+        u_evs.append((a_, b_))
+    torch.cuda.synchronize()
+    unify_us = 1e3 * float(np.median([a_.elapsed_time(b_) for a_, b_ in u_evs]))
+    unify_bytes = H * W * (3 * det.label_dtype.itemsize + 3)      # seg + pan read, pan re-read, 3 channels written
     t_dev, t_e2e = [v / 1e3 for v in P.max_over_ranks([sum(ms), sum(ms_e2e)], dev)]     # max over ranks
     value = world * args.steps / t_dev
     e2e = world * args.steps / t_e2e
@@ -316,6 +333,11 @@ def run_gpu_arm(args):
                         "h2d_gbps_measured": round(h2d_gbps, 2)},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "sequential_ms_per_pair": float(np.median(seq_ms)),
+                "next_rows": {"unify_pan": {"what": "get_unified_pan_result on the GPU (SURVEY 8f rank 1), one 1024x2048 frame, "
+                                                    "host-side id bookkeeping + 3 kernels, L2 flushed",
+                                            "us_per_frame": round(unify_us, 1), "algorithmic_bytes": unify_bytes,
+                                            "hbm_gbps": round(unify_bytes / (unify_us * 1e-6) / 1e9, 1),
+                                            "hbm_frac": round(unify_bytes / (unify_us * 1e-6) / 1e9 / peaks()["hbm"], 4)}},
                 "conv_flop_frac_whole_path": GFLOP_ALL_PAIR * (H * W) / float(H_FULL * W_FULL) * 1e9 * args.steps / t_dev / 1e12 / peaks()["tf_sus"]}
         if roof:
             line["roofline"] = roof

@@ -288,6 +288,19 @@ int vps_panoptic_fuse(const vps_tensor* fcn_score, const float* boxes, const int
                       int kcap, int num_stuff, int dummy, int H, int W, void* pano_out, void* sem_out,
                       int label_bytes, void* stream);
 
+/* ---- the step right after the hot path ------------------------------------------------------
+ * get_unified_pan_result for ONE frame (tools/dataset/cityscapes_vps.py:183-224): seg / pan = the [H,W] label maps of
+ * simple_test (uint8, or int64 of which the low byte is used -- the reference's collector casts to uint8,
+ * tools/test_vpq.py:52-56); cls_ind[k] = panoptic_cls_inds, obj_id[k] = track ids after the reference's duplicate
+ * re-numbering (host state, see vps_b200/postproc.py) or NULL -- both are HOST arrays (k <= 256, passed to the kernel by
+ * value); id_last_stuff = num_seg_classes - num_classes (10).
+ * out = uint8 [H,W,3] = (semantic, instance rank, track id + 1).  One histogram pass + a 256-entry look-up-table pass;
+ * ws >= vps_unify_pan_ws_bytes() bytes, 16-byte aligned. */
+int64_t vps_unify_pan_ws_bytes(void);
+int vps_unify_pan(const void* seg, const void* pan, int label_bytes, int H, int W, const int32_t* cls_ind,
+                  const int32_t* obj_id, int k, int id_last_stuff, int stuff_area_limit, uint8_t* out, void* ws,
+                  int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

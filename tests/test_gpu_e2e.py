@@ -159,3 +159,32 @@ def test_clip_runner_equals_direct_calls(models):
     for d, g in zip(direct, got):
         assert torch.equal(d[0], g[0].long()) and torch.equal(d[1], g[1].long())
         assert torch.equal(d[2], g[2]) and torch.equal(d[3], g[3])
+
+
+def test_clip_runner_unified_pan_result(models):
+    """ClipRunner(unify=True): the uint8 [H,W,3] image produced on the GPU right after each pair equals the oracle of the
+    reference's get_unified_pan_result applied, after the clip, to the collected maps / class ids / track ids."""
+    import numpy as np
+    from oracle import unify as U
+    from vps_b200.runner import ClipRunner
+    _, prod = models
+    prod.precision = "fp32"
+    H, W = 128, 256
+    frames = [make_pair(H, W, seed=s) for s in (21, 22, 23, 24)]
+    metas = [meta(10001 + f, H, W) for f in range(len(frames))]
+    try:
+        prod.label_dtype = torch.uint8
+        prod.reset_tracker()
+        pinned = [(a.pin_memory(), b.pin_memory()) for a, b in frames]
+        segs, pans, clss, objs, got = [], [], [], [], []
+        for r in ClipRunner(prod, "cuda:0", unify=True).run(pinned, metas):
+            segs.append(r[2]["fcn_outputs"][0].numpy().copy())
+            pans.append(r[2]["panoptic_outputs"][0].numpy().copy())
+            clss.append(r[2]["panoptic_cls_inds"].cpu().numpy())
+            objs.append(r[2]["panoptic_det_obj_ids"].cpu().numpy())
+            got.append(r[2]["pan_2ch"].numpy().copy())
+    finally:
+        prod.label_dtype = torch.int64
+    ref = U.get_unified_pan_result(segs, pans, clss, objs)
+    for g, e in zip(got, ref):
+        assert np.array_equal(g, e)

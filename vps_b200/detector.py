@@ -375,6 +375,9 @@ class PanopticFuseTrack(nn.Module):
             'panoptic_det_labels': torch.from_numpy(labels_h[keep_h].astype(np.int64)).to(dev),
             'panoptic_det_obj_ids': torch.from_numpy(ids_h[keep_h]).to(dev),
             'panoptic_outputs': pano[None, :h0, :w0],
+            # host copies of the two small per-instance arrays (already on the host here): the post-processing that follows
+            # the path (vps_b200.postproc.PanUnifier) needs them there
+            'host': dict(panoptic_cls_inds=cls_idx_h[keep_h].astype(np.int64), panoptic_det_obj_ids=ids_h[keep_h]),
         }
         bbox_results = bbox2result_with_id(det_rois_h[:, 1:], labels_h, ids_h)
         segm_results = [[] for _ in range(self.mask_head.num_classes - 1)]     # :484-485 (`or True`)

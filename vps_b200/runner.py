@@ -16,23 +16,39 @@ import torch
 
 
 class ClipRunner:
-    def __init__(self, det, device=None, depth=2):
+    def __init__(self, det, device=None, depth=2, unify=False):
         self.det = det
+        # unify: also run get_unified_pan_result (tools/dataset/cityscapes_vps.py:162-226) on the GPU for every pair
+        # (vps_b200.postproc.PanUnifier) and return the uint8 [H,W,3] image as pano_results['pan_2ch'] (host)
+        self.unifier = None
+        if unify:
+            from .postproc import PanUnifier
+            self.unifier = PanUnifier()
+        self._out2 = []
         self.dev = torch.device(device) if device is not None else next(det.parameters()).device
         self.copy = torch.cuda.Stream(self.dev)
         self.depth = depth
         self._out = []          # ring of pinned (pano, sem) host buffers
+        self._in, self._nup = [], 0   # ring of device input buffers
 
     def _upload(self, pair):
+        """H2D into a fixed ring of device buffers (no allocation in steady state).  Slot reuse is safe with 3 slots: the
+        upload of pair i+3 is issued after simple_test(i) returned, i.e. after everything that read slot i finished."""
         main = torch.cuda.current_stream(self.dev)
+        slot = self._nup % 3
+        self._nup += 1
+        while len(self._in) <= slot:
+            self._in.append(None)
+        bufs = self._in[slot]
+        if bufs is None or bufs[0].shape != pair[0].shape or bufs[0].dtype != pair[0].dtype:
+            bufs = self._in[slot] = (torch.empty(pair[0].shape, dtype=pair[0].dtype, device=self.dev),
+                                     torch.empty(pair[1].shape, dtype=pair[1].dtype, device=self.dev))
         with torch.cuda.stream(self.copy):
-            a = pair[0].to(self.dev, non_blocking=True)
-            b = pair[1].to(self.dev, non_blocking=True)
+            bufs[0].copy_(pair[0], non_blocking=True)
+            bufs[1].copy_(pair[1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy)
-        a.record_stream(main)
-        b.record_stream(main)
-        return a, b, ev
+        return bufs[0], bufs[1], ev
 
     def _host_buf(self, i, like):
         while len(self._out) <= i % self.depth:
@@ -80,16 +96,33 @@ class ClipRunner:
                     self.det.prefetch(staged[0], [cur[1]], ref_img=[staged[1]])
             r = self.det.simple_test(a, [meta], ref_img=[b])
             pano, sem = r[2]["panoptic_outputs"], r[2]["fcn_outputs"]
+            p2 = None
+            if self.unifier is not None:
+                hk = r[2].get("host", {})
+                p2 = self.unifier(sem, pano, hk.get("panoptic_cls_inds", r[2]["panoptic_cls_inds"]),
+                                  hk.get("panoptic_det_obj_ids", r[2].get("panoptic_det_obj_ids")))
             done = torch.cuda.Event()
             done.record(main)
             hp, hs, hev = self._host_buf(i, pano)
+            h2 = None
+            if p2 is not None:
+                while len(self._out2) <= i % self.depth:
+                    self._out2.append(None)
+                h2 = self._out2[i % self.depth]
+                if h2 is None or h2.shape != p2.shape:
+                    h2 = self._out2[i % self.depth] = torch.empty(p2.shape, dtype=torch.uint8).pin_memory()
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(done)
                 hp.copy_(pano, non_blocking=True)
                 hs.copy_(sem, non_blocking=True)
+                if p2 is not None:
+                    h2.copy_(p2, non_blocking=True)
                 hev.record(self.copy)
             pano.record_stream(self.copy)
             sem.record_stream(self.copy)
+            if p2 is not None:
+                p2.record_stream(self.copy)
+                r[2]["pan_2ch"] = h2
             if pending is not None:
                 pending[1].synchronize()               # the previous pair's maps are on the host now
                 yield pending[0]
