@@ -33,6 +33,8 @@ CASES = [
     (1, 16, 2, 40, 56, 3, 1, 1),         # FlowNetFusion predict_flow0 (bk=16 path)
     (1, 12, 64, 32, 64, 7, 2, 3),        # FlowNetS conv1 stem (cin 12): bk=16 implicit GEMM without s2d
     (1, 48, 32, 20, 36, 3, 1, 1),        # cin < 64
+    (1, 256, 256, 128, 256, 3, 1, 1),    # N = 256 halo layer, 256 tiles (two per CTA)
+    (1, 256, 256, 120, 248, 3, 1, 1),    # same, ragged tiles (240 tiles)
 ]
 
 
