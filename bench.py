@@ -277,6 +277,21 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     unify_us = 1e3 * float(np.median([a_.elapsed_time(b_) for a_, b_ in u_evs]))
     unify_bytes = H * W * (3 * det.label_dtype.itemsize + 3)      # seg + pan read, pan re-read, 3 channels written
+    # ---- the pixel-level step of the VPQ evaluator (np.unique over 64-bit (gt, pred) codes of a frame)
+    from vps_b200 import vpq as VPQ
+    rs = np.random.default_rng(0)
+    gt_np = (rs.integers(0, 40, size=(H // 16, W // 16)).repeat(16, 0).repeat(16, 1) * 1000 + 7).astype(np.int64)
+    pr_np = (rs.integers(0, 60, size=(H // 8, W // 8)).repeat(8, 0).repeat(8, 1) * 997).astype(np.int64)
+    gt_d, pr_d = torch.from_numpy(gt_np).to(dev), torch.from_numpy(pr_np).to(dev)
+    VPQ.frame_confusion(gt_d, pr_d)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(5):
+        VPQ.frame_confusion(gt_d, pr_d)                           # includes the read-back of the table (it syncs)
+    conf_us = (time.perf_counter() - t0) / 5 * 1e6
+    t0 = time.perf_counter()
+    np.unique(gt_np.astype(np.uint64) * np.uint64(VPQ.OFFSET) + pr_np.astype(np.uint64), return_counts=True)
+    conf_cpu_us = (time.perf_counter() - t0) * 1e6
     t_dev, t_e2e = [v / 1e3 for v in P.max_over_ranks([sum(ms), sum(ms_e2e)], dev)]     # max over ranks
     value = world * args.steps / t_dev
     e2e = world * args.steps / t_e2e
@@ -337,7 +352,10 @@ def run_gpu_arm(args):
                                                     "host-side id bookkeeping + 3 kernels, L2 flushed",
                                             "us_per_frame": round(unify_us, 1), "algorithmic_bytes": unify_bytes,
                                             "hbm_gbps": round(unify_bytes / (unify_us * 1e-6) / 1e9, 1),
-                                            "hbm_frac": round(unify_bytes / (unify_us * 1e-6) / 1e9 / peaks()["hbm"], 4)}},
+                                            "hbm_frac": round(unify_bytes / (unify_us * 1e-6) / 1e9 / peaks()["hbm"], 4)},
+                              "vpq_frame_confusion": {"what": "np.unique over (gt, pred) codes of one 1024x2048 frame (SURVEY 8f rank 2): "
+                                                              "pack + 64-bit radix sort + run-length encode + table read-back",
+                                                      "us_per_frame": round(conf_us, 1), "numpy_us_per_frame": round(conf_cpu_us, 1)}},
                 "conv_flop_frac_whole_path": GFLOP_ALL_PAIR * (H * W) / float(H_FULL * W_FULL) * 1e9 * args.steps / t_dev / 1e12 / peaks()["tf_sus"]}
         if roof:
             line["roofline"] = roof

@@ -301,6 +301,16 @@ int vps_unify_pan(const void* seg, const void* pan, int label_bytes, int H, int 
                   const int32_t* obj_id, int k, int id_last_stuff, int stuff_area_limit, uint8_t* out, void* ws,
                   int64_t ws_bytes, void* stream);
 
+/* ---- pixel-level step of the VPQ evaluator (tools/eval_vpq.py:138-145) --------------------------
+ * np.unique(gt.astype(uint64) * offset + pred, return_counts=True) over a tube of id maps (npix = nframes*H*W, device
+ * uint32): pairs_out (ascending) / counts_out must have room for npix entries, *nruns_dev receives the number of distinct
+ * pairs.  64-bit radix sort + run-length encode; ws >= vps_tube_confusion_ws_bytes(npix), 256-byte aligned.
+ * vps_rgb_to_id decodes an RGB-coded id image [npix,3] (r + 256 g + 65536 b, eval_vpq.py:87-89). */
+int64_t vps_tube_confusion_ws_bytes(int64_t npix);
+int vps_tube_confusion(const uint32_t* gt_ids, const uint32_t* pred_ids, int64_t npix, uint64_t offset, uint64_t* pairs_out,
+                       uint32_t* counts_out, int* nruns_dev, void* ws, int64_t ws_bytes, void* stream);
+int vps_rgb_to_id(const uint8_t* rgb, int64_t npix, uint32_t* ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

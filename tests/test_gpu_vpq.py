@@ -1,0 +1,66 @@
+"""GPU parity of the VPQ evaluator core: vps_b200.vpq (device confusion + host matching) vs the golden
+statistics produced by the reference's own evaluator, and vs the oracle on larger random tubes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(clips, categories, nframes):
+    from collections import defaultdict
+
+    from vps_b200 import vpq as P
+    stat = defaultdict(P.CatStat)
+    for frames in clips:
+        ev = P.VpqEvaluator(categories)
+        for gseg, pseg, gt, pr in frames:
+            ev.add_frame(gseg, pseg, torch.from_numpy(gt.astype(np.int64)).cuda(), torch.from_numpy(pr.astype(np.int64)).cuda())
+        for c, v in ev.compute(nframes).items():
+            stat[c] += v
+    return stat
+
+
+def test_vpq_matches_reference_golden(cuda):
+    from tests.test_vpq_cpu import CATEGORIES, load_clips
+    from vps_b200 import vpq as P
+    d, clips = load_clips()
+    for nframes in (1, 2, 3, 4):
+        stat = _run(clips, CATEGORIES, nframes)
+        ref = d["stat_k%d" % nframes]
+        for c in range(19):
+            assert [stat[c].tp, stat[c].fp, stat[c].fn] == ref[c, 1:].astype(int).tolist(), (nframes, c)
+            assert stat[c].iou == ref[c, 0], (nframes, c)            # same summation order -> identical float64
+        for row, t in enumerate((None, True, False)):
+            r, _ = P.pq_average(stat, CATEGORIES, isthing=t)
+            assert [r["pq"], r["sq"], r["rq"], float(r["n"])] == d["avg_k%d" % nframes][row].tolist()
+
+
+def test_frame_confusion_full_size_and_rgb(cuda):
+    """1024x2048 id maps: the device sort + run-length encode equals np.unique; rgb_to_id equals the reference's decode."""
+    from vps_b200 import vpq as P
+    rng = np.random.default_rng(11)
+    H, W = 1024, 2048
+    gt = rng.integers(0, 40, size=(H // 16, W // 16)).repeat(16, 0).repeat(16, 1).astype(np.uint32) * 1000 + 7
+    pr = rng.integers(0, 50, size=(H // 8, W // 8)).repeat(8, 0).repeat(8, 1).astype(np.uint32) * 997
+    gt[:3] = 0
+    pairs, counts = P.frame_confusion(torch.from_numpy(gt.astype(np.int64)).cuda(), torch.from_numpy(pr.astype(np.int64)).cuda())
+    rp, rc = np.unique(gt.astype(np.uint64) * np.uint64(P.OFFSET) + pr.astype(np.uint64), return_counts=True)
+    assert np.array_equal(pairs, rp) and np.array_equal(counts, rc)
+    rgb = rng.integers(0, 256, size=(33, 47, 3)).astype(np.uint8)
+    ids = P.rgb_to_id(torch.from_numpy(rgb).cuda()).cpu().numpy()
+    ref = rgb[..., 0].astype(np.uint32) + rgb[..., 1].astype(np.uint32) * 256 + rgb[..., 2].astype(np.uint32) * 65536
+    assert np.array_equal(ids.astype(np.uint32), ref)
+
+
+def test_vpq_matches_oracle_random_clip(cuda):
+    from oracle import vpq as V
+    from tests.golden.make_vpq_golden import CATEGORIES, synth_clip
+    from vps_b200 import vpq as P
+    rng = np.random.default_rng(5)
+    frames = synth_clip(rng, 5, 256, 512, n_inst=12)
+    for nframes in (1, 3):
+        ref = V.vpq_compute_single_core(frames, CATEGORIES, nframes=nframes)
+        got = _run([frames], CATEGORIES, nframes)
+        for c in range(19):
+            assert [got[c].tp, got[c].fp, got[c].fn, got[c].iou] == [ref[c].tp, ref[c].fp, ref[c].fn, ref[c].iou], (nframes, c)
