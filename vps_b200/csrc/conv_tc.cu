@@ -685,18 +685,17 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(afull_bar(s), 1);
-      mbar_init(aempty_bar(s), 1);
-      mbar_init(bfull_bar(s), 1);
-      mbar_init(bempty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS);
+  // prologue on the critical path of every launch: one barrier per thread of warp 2 (36 inits), descriptors prefetched by
+  // warp 0, TMEM allocated by warp 1 -- all concurrently
+  if (warp == 2) {
+    if (lane < 4 * MAX_STAGES) mbar_init(bar_base + 8u * lane, 1);                    // afull / aempty / bfull / bempty
+    if (lane >= 28) {                                                               // lanes 28..31: tfull[0,1], tempty[0,1]
+      const int a = lane & 1;
+      if (lane < 30) mbar_init(tfull_bar(a), 1); else mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
   }

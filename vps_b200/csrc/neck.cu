@@ -103,9 +103,10 @@ __global__ void flow_warp_kernel(vps::TV<const T> src, vps::TV<const TF> flow, v
 }
 
 // tcea_modules.py:52-61: one warp per pixel; out[:, 0:C] = fea0 * sigmoid(<emb0, emb_ref>), out[:, C:2C] = fea1 * ...
-template <typename T>
+template <typename T, int V>
 __global__ void tcea_temporal_kernel(vps::TV<const T> fea0, vps::TV<const T> fea1, vps::TV<const T> emb0,
                                      vps::TV<const T> emb1, vps::TV<const T> embr, vps::TV<T> out, int64_t npix) {
+  // a lane owns V consecutive channels (16-byte vectors when V > 1): one warp-wide load covers 32*V channels of a pixel
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -118,19 +119,27 @@ __global__ void tcea_temporal_kernel(vps::TV<const T> fea0, vps::TV<const T> fea
     const T* e1 = emb1.p + emb1.off(n, y, x);
     const T* er = embr.p + embr.off(n, y, x);
     float d0 = 0.f, d1 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float r = vps::ldf<T>(er + c);
-      d0 += vps::ldf<T>(e0 + c) * r;
-      d1 += vps::ldf<T>(e1 + c) * r;
+    for (int c = lane * V; c < C; c += 32 * V) {
+      float r[V], a[V], b[V];
+      vps::ldv<T, V>(er + c, r);
+      vps::ldv<T, V>(e0 + c, a);
+      vps::ldv<T, V>(e1 + c, b);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { d0 += a[j] * r[j]; d1 += b[j] * r[j]; }
     }
     for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
     const float p0 = 1.f / (1.f + expf(-d0)), p1 = 1.f / (1.f + expf(-d1));
     const T* f0 = fea0.p + fea0.off(n, y, x);
     const T* f1 = fea1.p + fea1.off(n, y, x);
     T* op = out.p + out.off(n, y, x);
-    for (int c = lane; c < C; c += 32) {
-      vps::stf<T>(op + c, vps::ldf<T>(f0 + c) * p0);
-      vps::stf<T>(op + C + c, vps::ldf<T>(f1 + c) * p1);
+    for (int c = lane * V; c < C; c += 32 * V) {
+      float a[V], b[V];
+      vps::ldv<T, V>(f0 + c, a);
+      vps::ldv<T, V>(f1 + c, b);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { a[j] *= p0; b[j] *= p1; }
+      vps::stv<T, V>(op + c, a);
+      vps::stv<T, V>(op + C + c, b);
     }
   }
 }
@@ -309,9 +318,16 @@ extern "C" int vps_tcea_temporal(const vps_tensor* fea0, const vps_tensor* fea1,
                     emb1->dtype == out->dtype && emb_ref->dtype == out->dtype, "tcea_temporal: dtype");
   const int64_t npix = (int64_t)out->n * out->h * out->w;
   if (!npix) return VPS_OK;
-  VPS_DISPATCH_T(out->dtype, T, (tcea_temporal_kernel<T><<<grid_for(npix * 32), 256, 0, (cudaStream_t)stream>>>(
-                                    vps::tv<const T>(*fea0), vps::tv<const T>(*fea1), vps::tv<const T>(*emb0),
-                                    vps::tv<const T>(*emb1), vps::tv<const T>(*emb_ref), vps::tv<T>(*out), npix)));
+  const int C = fea0->c;
+  const int Vw = out->dtype == VPS_F32 ? 4 : 8;
+  const bool vec = C % Vw == 0 && vps::vec_ok(*fea0, C) && vps::vec_ok(*fea1, C) && vps::vec_ok(*emb0, C) && vps::vec_ok(*emb1, C) &&
+                   vps::vec_ok(*emb_ref, C) && vps::vec_ok(*out, 2 * C);
+#define TT_LAUNCH(T, V) tcea_temporal_kernel<T, V><<<grid_for(npix * 32), 256, 0, (cudaStream_t)stream>>>(                \
+      vps::tv<const T>(*fea0), vps::tv<const T>(*fea1), vps::tv<const T>(*emb0), vps::tv<const T>(*emb1), vps::tv<const T>(*emb_ref), \
+      vps::tv<T>(*out), npix)
+  if (out->dtype == VPS_F32) { if (vec) TT_LAUNCH(float, 4); else TT_LAUNCH(float, 1); }
+  else { if (vec) TT_LAUNCH(__nv_bfloat16, 8); else TT_LAUNCH(__nv_bfloat16, 1); }
+#undef TT_LAUNCH
   VPS_CUDA_LAST("tcea_temporal");
   return VPS_OK;
 }
