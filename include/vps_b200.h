@@ -129,6 +129,16 @@ int vps_channelnorm(const vps_tensor* a, const vps_tensor* b, const vps_tensor* 
 int vps_flownet_input(const float* img_nchw, const float* ref_nchw, int H, int W, const float* std3,
                       const float* mean3, float rgb_max, double* sums_ws, const vps_tensor* x, void* stream);
 
+/* Fused construction of FlowNet2's stage inputs (flownet2.py:142-153): cat[12] = (x6 | resample2d(img1 = x6[3:6], flow) |
+ * flow / div | channelnorm(img0 - resampled)) with flow = bilinear upsample (align_corners False) of flow_lo [n,h,w,2] f32
+ * times mul; inv = 1 / div_flow.  One pass, one whole-pixel store; bit-identical to vps_resize_bilinear + vps_axpby +
+ * vps_resample2d + vps_channelnorm.  cat must be a full buffer (its channel padding is zeroed). */
+int vps_flownet_stage(const vps_tensor* x6, const vps_tensor* flow_lo, float mul, float inv, const vps_tensor* cat, void* stream);
+/* concat3 of flownet2.py:176-189: cat[11] = (img0 | sd_flow | s2_flow | |sd_flow| | |s2_flow| | |img0 - warp(img1, sd_flow)| |
+ * |img0 - warp(img1, s2_flow)|), the flows being nearest-upsampled low-resolution f32 flows times mul_s2 / mul_sd. */
+int vps_flownet_cat3(const vps_tensor* x6, const vps_tensor* s2_flow_lo, const vps_tensor* sd_flow_lo, float mul_s2, float mul_sd,
+                     const vps_tensor* cat, void* stream);
+
 /* nn.ConvTranspose2d(2, 2, 4, 2, 1): the `upsampled_flow*_to_*` layers of every FlowNet (FlowNetS.py:45-48,
  * FlowNetC.py:48-51, FlowNetSD.py:45-48, FlowNetFusion.py:34-35).  w_iohw_host = 64 HOST floats [ci][co][ky][kx],
  * bias_host = 2 HOST floats or NULL (they travel as kernel arguments); x [n,h,w,2] -> y [n,2h,2w,2] (a concat slice). */

@@ -65,3 +65,55 @@ def test_correlation_tensor_core(cuda, cfg):
         got = out.float().cpu().permute(0, 3, 1, 2)
         assert (got - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item()), (cfg, odt)
         assert (buf[..., :8] == 7.0).all() and (buf[..., 8 + D * D:] == 7.0).all()     # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_flownet_glue_fused_equals_separate_ops(cuda, dtype):
+    """vps_flownet_stage / vps_flownet_cat3 (one kernel per concat input of FlowNet2, flownet2.py:142-153, 176-189) are
+    bit-identical to the chains of resize / axpby / resample2d / channelnorm launches they replace."""
+    from vps_b200 import ops
+    from vps_b200.layers import empty_nhwc
+    g = torch.Generator().manual_seed(77)
+    n, H, W = 1, 64, 96
+    dev = torch.device("cuda:0")
+    x6 = empty_nhwc(n, H, W, 6, dtype, dev)
+    x6.copy_(torch.randn(n, H, W, 6, generator=g).to(dev))
+    x6[0, 0, 0, 0] = -0.0
+    img0, img1 = x6[..., 0:3], x6[..., 3:6]
+    flow2 = (torch.randn(n, H // 4, W // 4, 2, generator=g) * 3).to(dev)
+    sd2 = (torch.randn(n, H // 4, W // 4, 2, generator=g) * 40).to(dev)
+    div = 20.0
+    f32 = lambda c: torch.empty(n, H, W, c, dtype=torch.float32, device=dev)
+    # ---- stage
+    ref = empty_nhwc(n, H, W, 12, dtype, dev)
+    flow = f32(2)
+    ops.resize_bilinear(flow2, flow, mul=div)
+    ops.copy_scale(x6, ref[..., 0:6])
+    ops.resample2d(img1, flow, ref[..., 6:9])
+    ops.copy_scale(flow, ref[..., 9:11], 1.0 / div)
+    ops.channelnorm(img0, ref[..., 11:12], b=ref[..., 6:9])
+    got = empty_nhwc(n, H, W, 12, dtype, dev)
+    ops.flownet_stage(x6, flow2, div, 1.0 / div, got)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                       ref.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
+    # ---- concat3
+    ref3 = empty_nhwc(n, H, W, 11, dtype, dev)
+    s2f, sdf = f32(2), f32(2)
+    ops.resize_nearest(flow2, s2f, mul=div)
+    ops.resize_nearest(sd2, sdf, mul=1.0 / div)
+    ops.copy_scale(img0, ref3[..., 0:3])
+    ops.copy_scale(sdf, ref3[..., 3:5])
+    ops.copy_scale(s2f, ref3[..., 5:7])
+    ops.channelnorm(sdf, ref3[..., 7:8])
+    ops.channelnorm(s2f, ref3[..., 8:9])
+    warped = empty_nhwc(n, H, W, 3, dtype, dev)
+    ops.resample2d(img1, sdf, warped)
+    ops.channelnorm(img0, ref3[..., 9:10], b=warped)
+    ops.resample2d(img1, s2f, warped)
+    ops.channelnorm(img0, ref3[..., 10:11], b=warped)
+    got3 = empty_nhwc(n, H, W, 11, dtype, dev)
+    ops.flownet_cat3(x6, flow2, sd2, div, 1.0 / div, got3)
+    torch.cuda.synchronize()
+    assert torch.equal(got3.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                       ref3.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))

@@ -134,6 +134,15 @@ static inline dim3 pix_grid(int w, int chunks, int h, int n, int threads = 256) 
 }
 }  // namespace vps
 
+// bilinear blend with an explicit operation order: `hx*a + lx*b` leaves the compiler free to fuse either product into the
+// FMA, and two kernels computing the same interpolation (resize_bilinear / the fused FlowNet2 stage kernel) must agree bit
+// for bit
+__device__ __forceinline__ float vps_bilerp(float v00, float v01, float v10, float v11, float hx, float lx, float hy, float ly) {
+  const float top = __fmaf_rn(hx, v00, __fmul_rn(lx, v01));
+  const float bot = __fmaf_rn(hx, v10, __fmul_rn(lx, v11));
+  return __fmaf_rn(hy, top, __fmul_rn(ly, bot));
+}
+
 // per-thread coordinates for kernels launched with vps::pix_grid: V channels starting at `c`, pixel (n,y,x)
 #define VPS_PIX_COORDS(OUT, V, c_, x_, y_, n_)                           \
   const int chunks__ = (OUT).c / (V);                                    \

@@ -349,3 +349,176 @@ extern "C" int vps_flow_deconv(const vps_tensor* x, const float* w_iohw_host, co
   VPS_CUDA_LAST("flow_deconv");
   return VPS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused FlowNet2 glue.  Between its sub-networks FlowNet2 builds two concat inputs per pixel from 2-3 channel tensors
+// (flownet2.py:142-153 and :176-189).  As separate ops that is 5 / 11 launches of scalar 2-byte traffic at full
+// resolution; here ONE kernel per concat reads the pixel's inputs once and writes the whole 12 / 11-channel pixel.  The
+// arithmetic (and every rounding to the storage type T) is the same as in resize_bilinear / resize_nearest / axpby /
+// resample2d / channelnorm above and in pointwise.cu, expression by expression, so the results are bit-identical.
+namespace {
+template <typename T> __device__ __forceinline__ float round_T(float v);
+template <> __device__ __forceinline__ float round_T<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_T<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// resample2d of channels [c0, c0+3) of `src` at (x + dx, y + dy): border-clamped taps, weights not renormalised
+template <typename T>
+__device__ __forceinline__ void warp3(const vps::TV<const T>& src, int n, int x, int y, int c0, float dx, float dy, float (&o)[3]) {
+  const float xf = (float)x + dx, yf = (float)y + dy;
+  const float alpha = xf - floorf(xf), beta = yf - floorf(yf);
+  const int xL = max(min((int)floorf(xf), src.w - 1), 0);
+  const int xR = max(min((int)floorf(xf) + 1, src.w - 1), 0);
+  const int yT = max(min((int)floorf(yf), src.h - 1), 0);
+  const int yB = max(min((int)floorf(yf) + 1, src.h - 1), 0);
+  const T* pa = src.p + src.off(n, yT, xL) + c0;
+  const T* pb = src.p + src.off(n, yT, xR) + c0;
+  const T* pc = src.p + src.off(n, yB, xL) + c0;
+  const T* pd = src.p + src.off(n, yB, xR) + c0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float v = 0.f;
+    v += (1.f - alpha) * (1.f - beta) * vps::ldf<T>(pa + j);
+    v += (alpha) * (1.f - beta) * vps::ldf<T>(pb + j);
+    v += (1.f - alpha) * (beta) * vps::ldf<T>(pc + j);
+    v += (alpha) * (beta) * vps::ldf<T>(pd + j);
+    o[j] = round_T<T>(v);                         // resample2d stores T
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_pixel(T* op, const float* v, int c, int cs_pad) {
+  // whole-pixel store: c channels + zeroed padding up to cs_pad (the destination is a full buffer, never a slice)
+  if (sizeof(T) == 2 && cs_pad % 8 == 0 && (((uintptr_t)op) & 15) == 0) {
+    for (int g = 0; g < cs_pad / 8; ++g) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i0 = 8 * g + 2 * t;
+        __nv_bfloat162 b = __floats2bfloat162_rn(i0 < c ? v[i0] : 0.f, i0 + 1 < c ? v[i0 + 1] : 0.f);
+        pk[t] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(op) + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  } else {
+    for (int i = 0; i < c; ++i) vps::stf<T>(op + i, v[i]);
+  }
+}
+
+// concat(x6, resample(img1, flow), flow / div_flow, |img0 - resampled|) with flow = bilinear-upsampled flow_lo * mul
+template <typename T>
+__global__ void __launch_bounds__(256) flownet_stage_kernel(vps::TV<const T> x6, vps::TV<const float> flow_lo, float mul, float inv,
+                                                            vps::TV<T> cat, int cs_pad) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= cat.w) return;
+  // resize_bilinear (align_corners = False) of the 2-channel flow, times mul
+  const float sy = (float)flow_lo.h / (float)cat.h, sx = (float)flow_lo.w / (float)cat.w;
+  const float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f);
+  const float fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < flow_lo.h - 1 ? 1 : 0), x1 = x0 + (x0 < flow_lo.w - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float* f00 = flow_lo.p + flow_lo.off(n, y0, x0);
+  const float* f01 = flow_lo.p + flow_lo.off(n, y0, x1);
+  const float* f10 = flow_lo.p + flow_lo.off(n, y1, x0);
+  const float* f11 = flow_lo.p + flow_lo.off(n, y1, x1);
+  float fl[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) fl[j] = vps_bilerp(f00[j], f01[j], f10[j], f11[j], hx, lx, hy, ly) * mul;
+  float v[12];
+  const T* xp = x6.p + x6.off(n, y, x);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = 1.0f * vps::ldf<T>(xp + j) + 0.f;     // copy_scale(x6, cat[..., 0:6]) = axpby: alpha * a + 0
+  float wv[3];
+  warp3<T>(x6, n, x, y, 3, fl[0], fl[1], wv);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) v[6 + j] = wv[j];
+  v[9] = inv * fl[0] + 0.f; v[10] = inv * fl[1] + 0.f;                       // copy_scale(flow, cat[..., 9:11], 1 / div_flow)
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { float d = vps::ldf<T>(xp + j); d -= wv[j]; s += d * d; }
+  v[11] = sqrtf(s);                                                          // channelnorm(img0 - resampled)
+  store_pixel<T>(cat.p + cat.off(n, y, x), v, 12, cs_pad);
+}
+
+// concat3 = (img0, sd_flow, s2_flow, |sd_flow|, |s2_flow|, |img0 - warp(img1, sd_flow)|, |img0 - warp(img1, s2_flow)|)
+template <typename T>
+__global__ void __launch_bounds__(256) flownet_cat3_kernel(vps::TV<const T> x6, vps::TV<const float> s2_lo, vps::TV<const float> sd_lo,
+                                                           float mul_s2, float mul_sd, vps::TV<T> cat, int cs_pad) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= cat.w) return;
+  float s2[2], sd[2];
+  {   // resize_nearest * mul of both low-resolution flows
+    const float sy = (float)s2_lo.h / (float)cat.h, sx = (float)s2_lo.w / (float)cat.w;
+    const int ys = min((int)floorf((float)y * sy), s2_lo.h - 1), xs = min((int)floorf((float)x * sx), s2_lo.w - 1);
+    const float* p = s2_lo.p + s2_lo.off(n, ys, xs);
+    s2[0] = p[0] * mul_s2 + 0.f; s2[1] = p[1] * mul_s2 + 0.f;
+  }
+  {
+    const float sy = (float)sd_lo.h / (float)cat.h, sx = (float)sd_lo.w / (float)cat.w;
+    const int ys = min((int)floorf((float)y * sy), sd_lo.h - 1), xs = min((int)floorf((float)x * sx), sd_lo.w - 1);
+    const float* p = sd_lo.p + sd_lo.off(n, ys, xs);
+    sd[0] = p[0] * mul_sd + 0.f; sd[1] = p[1] * mul_sd + 0.f;
+  }
+  float v[11];
+  const T* xp = x6.p + x6.off(n, y, x);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) v[j] = 1.0f * vps::ldf<T>(xp + j) + 0.f;
+  v[3] = 1.0f * sd[0] + 0.f; v[4] = 1.0f * sd[1] + 0.f;
+  v[5] = 1.0f * s2[0] + 0.f; v[6] = 1.0f * s2[1] + 0.f;
+  {   // channelnorm of a 2-channel fp32 flow: the same accumulation loop as channelnorm_kernel
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { const float p = sd[j]; a += p * p; const float q = s2[j]; b += q * q; }
+    v[7] = sqrtf(a); v[8] = sqrtf(b);
+  }
+  float wv[3];
+  warp3<T>(x6, n, x, y, 3, sd[0], sd[1], wv);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { float d = vps::ldf<T>(xp + j); d -= wv[j]; s += d * d; }
+  v[9] = sqrtf(s);
+  warp3<T>(x6, n, x, y, 3, s2[0], s2[1], wv);
+  s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { float d = vps::ldf<T>(xp + j); d -= wv[j]; s += d * d; }
+  v[10] = sqrtf(s);
+  store_pixel<T>(cat.p + cat.off(n, y, x), v, 11, cs_pad);
+}
+}  // namespace
+
+static int cat_pad(const vps_tensor* cat) {      // channels a whole-pixel store may touch: only for a full (non-slice) buffer view
+  return cat->cs;
+}
+
+extern "C" int vps_flownet_stage(const vps_tensor* x6, const vps_tensor* flow_lo, float mul, float inv, const vps_tensor* cat, void* stream) {
+  VPS_CHECK_ARG(x6->c == 6 && flow_lo->c == 2 && flow_lo->dtype == VPS_F32 && cat->c == 12 && cat->dtype == x6->dtype &&
+                    cat->h == x6->h && cat->w == x6->w && cat->n == x6->n && flow_lo->n == x6->n, "flownet_stage: shapes");
+  if (!((int64_t)cat->n * cat->h * cat->w)) return VPS_OK;
+  dim3 grid((unsigned)vps::cdiv(cat->w, 256), (unsigned)cat->h, (unsigned)cat->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cat->dtype == VPS_F32)
+    flownet_stage_kernel<float><<<grid, 256, 0, st>>>(vps::tv<const float>(*x6), vps::tv<const float>(*flow_lo), mul, inv, vps::tv<float>(*cat), cat_pad(cat));
+  else
+    flownet_stage_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(vps::tv<const __nv_bfloat16>(*x6), vps::tv<const float>(*flow_lo), mul, inv,
+                                                             vps::tv<__nv_bfloat16>(*cat), cat_pad(cat));
+  VPS_CUDA_LAST("flownet_stage");
+  return VPS_OK;
+}
+
+extern "C" int vps_flownet_cat3(const vps_tensor* x6, const vps_tensor* s2_flow_lo, const vps_tensor* sd_flow_lo, float mul_s2, float mul_sd,
+                                const vps_tensor* cat, void* stream) {
+  VPS_CHECK_ARG(x6->c == 6 && s2_flow_lo->c == 2 && sd_flow_lo->c == 2 && s2_flow_lo->dtype == VPS_F32 && sd_flow_lo->dtype == VPS_F32 &&
+                    cat->c == 11 && cat->dtype == x6->dtype && cat->h == x6->h && cat->w == x6->w && cat->n == x6->n, "flownet_cat3: shapes");
+  if (!((int64_t)cat->n * cat->h * cat->w)) return VPS_OK;
+  dim3 grid((unsigned)vps::cdiv(cat->w, 256), (unsigned)cat->h, (unsigned)cat->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cat->dtype == VPS_F32)
+    flownet_cat3_kernel<float><<<grid, 256, 0, st>>>(vps::tv<const float>(*x6), vps::tv<const float>(*s2_flow_lo), vps::tv<const float>(*sd_flow_lo),
+                                                     mul_s2, mul_sd, vps::tv<float>(*cat), cat_pad(cat));
+  else
+    flownet_cat3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(vps::tv<const __nv_bfloat16>(*x6), vps::tv<const float>(*s2_flow_lo),
+                                                            vps::tv<const float>(*sd_flow_lo), mul_s2, mul_sd, vps::tv<__nv_bfloat16>(*cat),
+                                                            cat_pad(cat));
+  VPS_CUDA_LAST("flownet_cat3");
+  return VPS_OK;
+}

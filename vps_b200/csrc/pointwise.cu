@@ -73,7 +73,7 @@ __global__ void resize_bilinear_kernel(vps::TV<const TI> src, vps::TV<TO> out, f
   vps::ldv<TI, V>(src.p + src.off(n, y1, x0) + c, v10);
   vps::ldv<TI, V>(src.p + src.off(n, y1, x1) + c, v11);
 #pragma unroll
-  for (int j = 0; j < V; ++j) v00[j] = (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j])) * mul;
+  for (int j = 0; j < V; ++j) v00[j] = vps_bilerp(v00[j], v01[j], v10[j], v11[j], hx, lx, hy, ly) * mul;
   vps::stv<TO, V>(out.p + out.off(n, y, x) + c, v00);
 }
 

@@ -206,6 +206,7 @@ class FlowNet2(_Prepared):
     def __init__(self, rgb_max=255.0, div_flow=20.0):
         super().__init__()
         self.rgb_max, self.div_flow = rgb_max, div_flow
+        self.fused_glue = True       # build the inter-network concat inputs with one kernel each (ops.flownet_stage / flownet_cat3)
         self.flownetc = _FlowNetC()
         self.flownets_1 = _FlowNetS()
         self.flownets_2 = _FlowNetS()
@@ -229,6 +230,8 @@ class FlowNet2(_Prepared):
         def stage(flow2):
             """concat(x, resampled_img1, flow/div_flow, norm_diff) (flownet2.py:142-153) for FlowNetS."""
             cat = empty_nhwc(n, H, W, 12, dt, dev)
+            if self.fused_glue:      # one kernel builds the 12-channel pixel (bit-identical to the five ops below)
+                return ops.flownet_stage(x6, flow2, self.div_flow, 1.0 / self.div_flow, cat)
             flow = f32(2)
             ops.resize_bilinear(flow2, flow, mul=self.div_flow)       # upsample(flow2 * div_flow)
             ops.copy_scale(x6, cat[..., 0:6])
@@ -250,6 +253,12 @@ class FlowNet2(_Prepared):
 
         # concat3 = (img0, sd_flow, s2_flow, |sd_flow|, |s2_flow|, |img0 - warp_sd|, |img0 - warp_s2|) flownet2.py:189
         cat3 = empty_nhwc(n, H, W, 11, dt, dev)
+        if self.fused_glue:
+            ops.flownet_cat3(x6, s2_flow2, sd_flow2, self.div_flow, 1.0 / self.div_flow, cat3)
+            out = self.flownetfusion(cat3)
+            if taps is not None:
+                taps.update(c_flow2=c_flow2, s1_flow2=s1_flow2, s2_flow2=s2_flow2, sd_flow2=sd_flow2, concat1=cat1, concat3=cat3)
+            return out
         s2_flow, sd_flow = f32(2), f32(2)
         ops.resize_nearest(s2_flow2, s2_flow, mul=self.div_flow)          # upsample4(flow2 * div_flow)
         ops.resize_nearest(sd_flow2, sd_flow, mul=1.0 / self.div_flow)    # upsample3(flow2 / div_flow)

@@ -308,6 +308,17 @@ def flownet_input(img_nchw, ref_nchw, std3, mean3, rgb_max, sums_ws, x):
     return x
 
 
+def flownet_stage(x6, flow_lo, mul, inv, cat):
+    check(lib().vps_flownet_stage(_bt(x6), _bt(flow_lo), C.c_float(mul), C.c_float(inv), _bt(cat), stream()), "flownet_stage")
+    return cat
+
+
+def flownet_cat3(x6, s2_flow_lo, sd_flow_lo, mul_s2, mul_sd, cat):
+    check(lib().vps_flownet_cat3(_bt(x6), _bt(s2_flow_lo), _bt(sd_flow_lo), C.c_float(mul_s2), C.c_float(mul_sd), _bt(cat), stream()),
+          "flownet_cat3")
+    return cat
+
+
 # ------------------------------------------------------------------ BFPTcea / DCN
 def bfp_gather(levels, out):
     arr = (VpsTensor * len(levels))(*[vt(l) for l in levels])
