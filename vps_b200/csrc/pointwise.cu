@@ -202,16 +202,30 @@ __global__ void __launch_bounds__(256) gn_stats_vec_kernel(vps::TV<const TI> x, 
   double ds[2] = {0.0, 0.0}, dss[2] = {0.0, 0.0};
   int cnt = 0;
   if (row < rows) {
-    for (int64_t pix = (int64_t)blockIdx.x * rows + row; pix < npix; pix += (int64_t)gridDim.x * rows) {
-      float v[V];
-      vps::ldv<TI, V>(x.p + ((int64_t)n * npix + pix) * x.cs + c0, v);
+    // 4 independent 16-byte loads in flight per thread (one was latency bound: 1.7 TB/s on an L2/HBM-resident map)
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * rows;
+    for (int64_t pix = (int64_t)blockIdx.x * rows + row; pix < npix; pix += U * stride) {
+      float v[U][V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const int gi = (V > 1 && j >= cg) ? 1 : 0;            // cg < V only when V == 2 * cg (no runtime division)
-        s[gi] += v[j];
-        ss[gi] += v[j] * v[j];
+      for (int u = 0; u < U; ++u) {
+        const int64_t q = pix + u * stride;
+        if (q < npix) vps::ldv<TI, V>(x.p + ((int64_t)n * npix + q) * x.cs + c0, v[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[u][j] = 0.f;
+        }
       }
-      if (++cnt == 64) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int gi = (V > 1 && j >= cg) ? 1 : 0;          // cg < V only when V == 2 * cg (no runtime division)
+          s[gi] += v[u][j];
+          ss[gi] += v[u][j] * v[u][j];
+        }
+      }
+      if (++cnt == 16) {
         ds[0] += s[0]; ds[1] += s[1]; dss[0] += ss[0]; dss[1] += ss[1];
         s[0] = s[1] = ss[0] = ss[1] = 0.f; cnt = 0;
       }

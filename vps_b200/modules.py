@@ -267,11 +267,14 @@ class BFPTcea(_Prepared):
         ccat = c + 81 + 2
         cat = empty_nhwc(n, h, w, ccat, dt, dev)
         bsf = cat[..., :c]
+        br = ops.Branch("bfp_ref")                 # the reference frame's gather + warp next to the current frame's gather
+        with br:
+            ref_bsf = empty_nhwc(n, h, w, c, dt, dev)
+            ops.bfp_gather(list(ref_inputs), ref_bsf)
+            warp = empty_nhwc(n, h, w, c, dt, dev)
+            ops.flow_warp(ref_bsf, flow_init, warp)
         ops.bfp_gather(list(inputs), bsf)
-        ref_bsf = empty_nhwc(n, h, w, c, dt, dev)
-        ops.bfp_gather(list(ref_inputs), ref_bsf)
-        warp = empty_nhwc(n, h, w, c, dt, dev)
-        ops.flow_warp(ref_bsf, flow_init, warp)
+        br.join(warp, ref_bsf)
         ops.correlation(bsf, warp, cat[..., c:c + 81], 4, 4, 1, 1)
         ops.copy_scale(flow_init, cat[..., c + 81:c + 83])
         t = self.k_flow[0](cat)
