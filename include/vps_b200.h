@@ -320,6 +320,9 @@ int64_t vps_tube_confusion_ws_bytes(int64_t npix);
 int vps_tube_confusion(const uint32_t* gt_ids, const uint32_t* pred_ids, int64_t npix, uint64_t offset, uint64_t* pairs_out,
                        uint32_t* counts_out, int* nruns_dev, void* ws, int64_t ws_bytes, void* stream);
 int vps_rgb_to_id(const uint8_t* rgb, int64_t npix, uint32_t* ids, void* stream);
+/* segment ids of a unified 3-channel result [npix,3] (vps_unify_pan): 1000 * semantic + track channel + 1, VOID (semantic
+ * 255) -> 0 -- the keying of converter_2ch_track_core (tools/dataset/cityscapes_vps.py:104-111) without its random colours */
+int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, uint32_t* ids, void* stream);
 
 #ifdef __cplusplus
 }

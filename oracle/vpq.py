@@ -146,3 +146,17 @@ def pq_average(stat, categories, isthing=None):
         per_class[label] = {"pq": pq_c, "sq": sq_c, "rq": rq_c, "iou": c.iou, "tp": c.tp, "fp": c.fp, "fn": c.fn}
         pq += pq_c; sq += sq_c; rq += rq_c
     return {"pq": pq / n, "sq": sq / n, "rq": rq / n, "n": n}, per_class
+
+
+def segments_from_pan2ch(pan_2ch):
+    """numpy counterpart of vps_b200.vpq.segments_from_pan2ch (keying of converter_2ch_track_core,
+    tools/dataset/cityscapes_vps.py:96-131, without its random colours): returns (ids uint32 [H,W], segments)."""
+    p = np.asarray(pan_2ch).astype(np.uint32)
+    ids = np.where(p[..., 0] == 255, 0, 1000 * p[..., 0] + p[..., 2] + 1).astype(np.uint32)
+    segs = []
+    for i, a in zip(*np.unique(ids, return_counts=True)):
+        if i == VOID:
+            continue
+        segs.append({"id": int(i), "category_id": int((int(i) - 1) // 1000), "iscrowd": 0, "area": int(a)})
+    return ids, segs
+

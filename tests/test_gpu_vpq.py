@@ -64,3 +64,67 @@ def test_vpq_matches_oracle_random_clip(cuda):
         got = _run([frames], CATEGORIES, nframes)
         for c in range(19):
             assert [got[c].tp, got[c].fp, got[c].fn, got[c].iou] == [ref[c].tp, ref[c].fp, ref[c].fn, ref[c].iou], (nframes, c)
+
+
+def _oracle_clip(oracle, frames, H, W):
+    """oracle simple_test over a clip + oracle unify -> list of (ids, segments) per frame"""
+    from oracle import unify as U
+    from oracle import vpq as V
+    segs, pans, clss, objs = [], [], [], []
+    for f, (a, b) in enumerate(frames):
+        r = oracle.simple_test(a, dict(iid=10001 + f, img_shape=(H, W, 3)), b, {})
+        p = r[2]
+        segs.append(p["fcn_outputs"][0].numpy().astype(np.uint8))
+        pans.append(p["panoptic_outputs"][0].numpy().astype(np.uint8))
+        clss.append(np.asarray(p["panoptic_cls_inds"]))
+        objs.append(np.asarray(p["panoptic_det_obj_ids"]))
+    uni = U.get_unified_pan_result(segs, pans, clss, objs, stuff_area_limit=256)
+    return [V.segments_from_pan2ch(u) for u in uni]
+
+
+def _product_clip(prod, frames, H, W, precision):
+    from tests.e2e_util import meta
+    from vps_b200 import vpq as P
+    from vps_b200.postproc import PanUnifier
+    prod.precision = precision
+    prod.label_dtype = torch.uint8
+    prod.reset_tracker()
+    uni = PanUnifier(stuff_area_limit=256)
+    out = []
+    try:
+        for f, (a, b) in enumerate(frames):
+            r = prod.simple_test(a.cuda(), [meta(10001 + f, H, W)], ref_img=[b.cuda()])
+            p2 = uni(r[2]["fcn_outputs"], r[2]["panoptic_outputs"], r[2]["host"]["panoptic_cls_inds"], r[2]["host"]["panoptic_det_obj_ids"])
+            out.append(P.segments_from_pan2ch(p2))
+    finally:
+        prod.label_dtype = torch.int64
+        prod.precision = "fp32"
+    return out
+
+
+def test_vpq_parity_of_the_whole_chain(cuda):
+    """BASELINE metric 'VPQ parity': a 5-frame clip through the product (model -> unified pan result -> segments, all on
+    the GPU) evaluated with the GPU VPQ evaluator against the same chain of the oracle on the CPU as ground truth.
+    fp32 mode: every tube matches with IoU 1 (VPQ = 100 for all window lengths).  bf16 mode: the agreement is reported (with
+    random-init weights the logits are noise-like, so small perturbations move whole segments: measured PQ 0.71 at k = 1)
+    and only guarded against collapse -- it is the accuracy cost of the fast mode in the units the reference is evaluated in."""
+    from tests.e2e_util import build_models, make_pair
+    from tests.test_vpq_cpu import CATEGORIES
+    from vps_b200 import vpq as P
+    oracle, prod = build_models("C", 0, "fp32", "cuda:0")
+    H, W = 128, 256
+    frames = [make_pair(H, W, seed=s) for s in (51, 52, 53, 54, 55)]
+    gt = _oracle_clip(oracle, frames, H, W)
+    for precision, floor in (("fp32", 1.0), ("bf16", 0.30)):
+        pred = _product_clip(prod, frames, H, W, precision)
+        ev = P.VpqEvaluator(CATEGORIES)
+        for (gi, gs), (pi, ps) in zip(gt, pred):
+            ev.add_frame(gs, ps, torch.from_numpy(gi.astype(np.int64)).cuda(), pi)
+        for nframes in (1, 2, 3):
+            stat = ev.compute(nframes)
+            res, _ = P.pq_average(stat, CATEGORIES, isthing=None)
+            print("VPQ agreement %s k=%d: PQ %.4f SQ %.4f RQ %.4f (n=%d)" % (precision, nframes, res["pq"], res["sq"], res["rq"], res["n"]))
+            if precision == "fp32":
+                assert res["pq"] == 1.0 and res["sq"] == 1.0 and res["rq"] == 1.0, (nframes, res)
+            else:
+                assert res["pq"] >= floor, (nframes, res)

@@ -18,6 +18,16 @@ __global__ void rgb_to_id_kernel(const uint8_t* __restrict__ rgb, int64_t n, uin
     ids[i] = (uint32_t)rgb[3 * i] + 256u * rgb[3 * i + 1] + 65536u * rgb[3 * i + 2];
 }
 
+// segment id of a pixel of the unified 3-channel result (semantic, instance rank, track id): the reference's converter
+// (tools/dataset/cityscapes_vps.py:104-111) keys segments by OFFSET * semantic + track channel and skips VOID (semantic 255);
+// id 0 stays VOID, so the key is shifted by one
+__global__ void pan2ch_ids_kernel(const uint8_t* __restrict__ p2, int64_t n, uint32_t* __restrict__ ids) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t sem = p2[3 * i], trk = p2[3 * i + 2];
+    ids[i] = sem == 255u ? 0u : 1000u * sem + trk + 1u;
+  }
+}
+
 struct Layout { size_t keys, sorted, temp, temp_bytes, total; };
 Layout layout(int64_t n, int cap) {
   Layout l;
@@ -37,6 +47,14 @@ Layout layout(int64_t n, int cap) {
 }  // namespace
 
 extern "C" int64_t vps_tube_confusion_ws_bytes(int64_t npix) { return npix > 0 ? (int64_t)layout(npix, 0).total : 256; }
+
+extern "C" int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, uint32_t* ids, void* stream) {
+  if (npix <= 0) return VPS_OK;
+  const int blocks = (int)((npix + 255) / 256 > 148 * 16 ? 148 * 16 : (npix + 255) / 256);
+  pan2ch_ids_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pan_2ch, npix, ids);
+  VPS_CUDA_LAST("pan2ch_ids");
+  return VPS_OK;
+}
 
 extern "C" int vps_rgb_to_id(const uint8_t* rgb, int64_t npix, uint32_t* ids, void* stream) {
   if (npix <= 0) return VPS_OK;

@@ -60,6 +60,24 @@ def rgb_to_id(rgb):
     return out
 
 
+def segments_from_pan2ch(pan_2ch, num_stuff=11):
+    """Unified 3-channel result (uint8 CUDA [H,W,3], vps_b200.postproc.PanUnifier) -> (id map int32 CUDA [H,W], segments list).
+    The reference's converter (tools/dataset/cityscapes_vps.py:96-131) keys a segment by 1000 * semantic + track channel, skips
+    VOID and gives it a random colour as id; VPQ is invariant to the id values, so the key itself (+1, 0 = VOID) is the id
+    here.  category_id = semantic class, iscrowd = 0, area = pixel count."""
+    assert pan_2ch.is_cuda and pan_2ch.dtype == torch.uint8 and pan_2ch.shape[-1] == 3
+    pan_2ch = pan_2ch.contiguous()
+    ids = torch.empty(pan_2ch.shape[:-1], dtype=torch.int32, device=pan_2ch.device)
+    ops.check(lib().vps_pan2ch_ids(ops._ptr(pan_2ch), C.c_int64(ids.numel()), ops._ptr(ids), ops.stream()), "pan2ch_ids")
+    pairs, counts = frame_confusion(torch.zeros_like(ids), ids)      # gt = 0: the pair code is the id itself
+    segs = []
+    for i, a in zip(pairs.tolist(), counts.tolist()):
+        if i == VOID:
+            continue
+        segs.append({"id": int(i), "category_id": int((i - 1) // 1000), "iscrowd": 0, "area": int(a)})
+    return ids, segs
+
+
 def _merge_segments(seg_list):
     out = {}
     for el in seg_list:                                          # eval_vpq.py:90-101
