@@ -84,6 +84,7 @@ class PanopticFuseTrack(nn.Module):
     def prepare(self, force=False):
         if force:
             self._graphs.clear()          # captured graphs reference the old packed weights
+            self._pf_queue, self._tail_done = [], [None, None]
         for m in (self.backbone, self.neck, self.extra_neck, self.panopticFPN, self.rpn_head, self.bbox_head,
                   self.track_head, self.mask_head, self.flownet2):
             m.prepare(force)
