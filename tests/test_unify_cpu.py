@@ -38,3 +38,16 @@ def test_dedup_track_ids_counter_runs_across_frames():
     assert a.tolist() == [101, 102, 100, 3, 5] and m == 103       # last occurrence keeps the id, earlier ones walk backwards
     b, m = U.dedup_track_ids(np.array([7, 7]), m)
     assert b.tolist() == [103, 7] and m == 104
+
+
+def test_product_dedup_matches_oracle():
+    """PanUnifier's host-side duplicate-track-id bookkeeping (the only state of the unify row) equals the oracle's over a
+    sequence of frames (no GPU needed)."""
+    from oracle import unify as U
+    from vps_b200.postproc import PanUnifier
+    rng = np.random.default_rng(1)
+    u, m = PanUnifier(), 100
+    for _ in range(20):
+        ids = rng.integers(0, 12, size=int(rng.integers(0, 15)))
+        ref, m = U.dedup_track_ids(ids, m)
+        assert u.dedup_track_ids(ids).tolist() == ref.tolist() and u.max_oid == m

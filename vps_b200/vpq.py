@@ -96,7 +96,12 @@ class VpqEvaluator:
         self.frames = []            # (gt_segms, pred_segms, pairs, counts)
 
     def add_frame(self, gt_segments, pred_segments, gt_ids, pred_ids):
+        """gt_ids / pred_ids: CUDA id maps of one sampled frame"""
         pairs, counts = frame_confusion(gt_ids, pred_ids)
+        self.add_frame_table(gt_segments, pred_segments, pairs, counts)
+
+    def add_frame_table(self, gt_segments, pred_segments, pairs, counts):
+        """host part of add_frame: (pairs, counts) = the frame's sorted (gt * 2^24 + pred) codes and their pixel counts"""
         gt_segms, pred_segms = _merge_segments(gt_segments), _merge_segments(pred_segments)
         # predicted areas are recounted from the id map + sanity checks (eval_vpq.py:102-116)
         area = defaultdict(int)
