@@ -151,7 +151,7 @@ def run_reference_arm(args):
         return
     threads = host_threads()
     m = oracle_model()
-    (Hs, Ws), frac, _ = pick_sample(m, threads, per_step_budget_s=10.0)
+    (Hs, Ws), frac, _ = pick_sample(m, threads, per_step_budget_s=float(os.environ.get("VPS_BENCH_STEP_BUDGET_S", "10.0")))
     times = time_oracle(m, Hs, Ws, args.warmup + args.steps, threads)[args.warmup:]
     t = float(np.mean(times))
     v = frac / t
