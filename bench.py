@@ -5,9 +5,12 @@
   python bench.py --impl reference --gpus N --steps K ...  # reference arm: the oracle port on the host CPU cores
 
 One step = one `simple_test` call = one frame pair -> one panoptic frame.  Prints ONE JSON line (rank 0).
-  value      : pairs/s, inputs already resident in HBM, device-timed (CUDA events), max over ranks, summed over ranks
-  e2e        : same through the public detector call with HOST (pinned) frames: H2D of both frames and D2H of the
-               label maps inside the timed region
+  value      : pairs/s over ONE device-timed region (CUDA events) of K steps through the public clip loop
+               (vps_b200.runner.ClipRunner), inputs already resident in HBM, max over ranks, summed over ranks
+  e2e        : the same region with HOST (pinned) frames: H2D of both frames and D2H of the label maps of every step
+               inside the timed region
+  sequential_ms_per_pair : one pair at a time, L2 flushed in between (latency)
+  next_rows  : the first rows past the hot path: unified pan result, VPQ frame confusion
   roofline   : the dominant kernel (tcgen05 implicit-GEMM conv, all launches of a step): algorithmic conv FLOPs /
                summed kernel time, against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json
   cpu_baseline: the oracle (CPU port of the reference math) on a bounded sample, host cores
