@@ -21,10 +21,13 @@ def models(cuda):
     return build_models("C", 0, "fp32", "cuda:0")
 
 
-def test_fp32_clip_matches_oracle(models):
+@pytest.mark.parametrize("precision", ["tc32", "fp32"])
+def test_fp32_clip_matches_oracle(models, precision):
+    """tc32 = the tensor-core parity precision (the benchmarked headline mode); fp32 = its CUDA-core debugging twin."""
     oracle, prod = models
-    prod.precision = "fp32"
+    prod.precision = precision
     prod.reset_tracker()
+    oracle.prev_bboxes = None
     H, W = 128, 256
     img, ref = make_pair(H, W)
     for iid, (a, b) in ((10001, (img, ref)), (10002, (ref, img)), (10003, (img, ref))):
@@ -41,9 +44,10 @@ def test_fp32_clip_matches_oracle(models):
         assert rep["pano_agree"] == 1.0 and rep["sem_agree"] == 1.0, rep                        # label maps bit-exact
 
 
-def test_fp32_clip_matches_reference_golden(models):
+@pytest.mark.parametrize("precision", ["tc32", "fp32"])
+def test_fp32_clip_matches_reference_golden(models, precision):
     _, prod = models
-    prod.precision = "fp32"
+    prod.precision = precision
     prod.reset_tracker()
     g = np.load(GOLD)
     H, W = int(g["H"]), int(g["W"])

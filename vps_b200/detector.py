@@ -10,7 +10,9 @@ names, so `state_dict()` keys match a reference checkpoint.  Differences by desi
     (NMS mask download, MaskROI numpy, MaskRemoval numpy/cv2, SegTerm numpy, tracker loops) are kernels.
     Two 4-byte counters (number of detections, tracker memory size) are read back per frame to size the
     data-dependent launches.
-  * `precision`: "bf16" (tcgen05 tensor cores; the benchmarked mode) or "fp32" (CUDA-core fp32, parity mode).
+  * `precision`: "tc32" (fp32 activations, tcgen05 tensor cores with split operands: tf32 + two bf16 correction
+    products per K slab -- the parity mode, label maps / ids bit-exact vs the oracle), "bf16" (bf16 activations, one
+    tensor-core pass: fastest, ~1e-2 relative on features) or "fp32" (CUDA-core fp32 FMA: debugging reference).
 """
 import numpy as np
 import torch
@@ -269,6 +271,7 @@ class PanopticFuseTrack(nn.Module):
         if not (self.use_cuda_graph and ops.PROFILE is None):
             return
         self.prepare()
+        ops.F32_TC[0] = self.precision == "tc32"
         cur = torch.cuda.current_stream(img.device)
         if self._pf_stream is None:
             self._pf_stream = torch.cuda.Stream(img.device)
@@ -299,6 +302,8 @@ class PanopticFuseTrack(nn.Module):
         meta = img_meta[0] if isinstance(img_meta, (list, tuple)) else img_meta
         assert 'city' in meta['filename'] and 'iid' in meta            # :375
         self.prepare()
+        assert self.precision in ("tc32", "bf16", "fp32"), self.precision
+        ops.F32_TC[0] = self.precision == "tc32"
         dev = img.device
         n, _, H, W = img.shape
         assert n == 1

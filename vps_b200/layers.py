@@ -33,7 +33,10 @@ class Conv:
                 (w + 2 * self.pad - self.pk.kw) // self.stride + 1)
 
     def tc_ok(self, x):
-        # tensor-core path: bf16 activations with a 16-byte aligned base and pixel stride (TMA requirement)
+        # tensor-core path: bf16 activations (or fp32 in the tc32 parity precision) with a 16-byte aligned base and
+        # pixel stride (TMA requirement)
+        if x.dtype == torch.float32:
+            return ops.f32_tc_ok(x)
         return x.dtype == torch.bfloat16 and ops.vt(x).cs % 8 == 0 and x.data_ptr() % 16 == 0
 
     def __call__(self, x, y=None, act=None, res=None, res_after_act=False, out_scale=1.0, out_dtype=None):
@@ -42,7 +45,7 @@ class Conv:
         if y is None:
             y = empty_nhwc(n, oh, ow, self.cout, out_dtype or x.dtype, x.device)
         act = self.act if act is None else act
-        if x.dtype == torch.bfloat16 and not self.tc_ok(x):
+        if (x.dtype == torch.bfloat16 or ops.F32_TC[0]) and not self.tc_ok(x):
             # mis-aligned channel slice (e.g. frame 2 of the 6-channel FlowNet input): re-base it once
             xa = empty_nhwc(n, h, w, x.shape[3], x.dtype, x.device)
             ops.copy_scale(x, xa)
@@ -73,7 +76,7 @@ class StemConv7x7s2:
         self.cin, self.cout, self.act = ci, co, act
 
     def __call__(self, x, y=None, act=None, out_dtype=None):
-        if x.dtype != torch.bfloat16:
+        if x.dtype != torch.bfloat16 and not ops.F32_TC[0]:
             return self.plain(x, y, act=act, out_dtype=out_dtype)
         n, h, w, c = x.shape
         xs = empty_nhwc(n, (h + 1) // 2, (w + 1) // 2, 4 * c, x.dtype, x.device)
@@ -94,6 +97,7 @@ class _PhaseDeconv:
         # weight_iohw: [cin, cout, k, k] fp32 on device
         self.cin, self.cout = weight_iohw.shape[:2]
         self.k = k
+        self._shared32 = None
         self.phases = []
         w_oihw = weight_iohw.permute(1, 0, 2, 3)
         for py in range(2):
@@ -111,11 +115,13 @@ class _PhaseDeconv:
     def __call__(self, x, y, act=ACT_NONE, slope=0.1, out_scale=1.0):
         n, h, w, _ = x.shape
         use_tc = (x.dtype == torch.bfloat16 and self.cin >= 16 and ops.vt(x).cs % 8 == 0
-                  and x.data_ptr() % 16 == 0)
+                  and x.data_ptr() % 16 == 0) or (self.cin >= 16 and ops.f32_tc_ok(x))
         if use_tc:      # all four stride phases in one persistent launch
+            if x.dtype == torch.float32 and self._shared32 is None:
+                self._shared32 = ops.pack_tc32([ph[3] for ph in self.phases])
             ops.conv2d_tc_multi(x, [ph[3] for ph in self.phases], y, [ph[2] for ph in self.phases],
                                 [(2, ph[0], 2, ph[1]) for ph in self.phases], act=act, slope=slope,
-                                out_scale=out_scale, oh=h, ow=w)
+                                out_scale=out_scale, oh=h, ow=w, shared32=self._shared32)
             return y
         for py, px, pad, pk in self.phases:
             ops.conv2d(x, pk, y, stride=1, pad_hw=pad, act=act, slope=slope, oh=h, ow=w,
@@ -147,6 +153,6 @@ class Linear:
             y2d = torch.empty(m, (self.cout + 7) // 8 * 8, dtype=out_dtype or x2d.dtype, device=x2d.device)[:, :self.cout]
         x4 = x2d.unsqueeze(0).unsqueeze(0)
         y4 = y2d.unsqueeze(0).unsqueeze(0)
-        use_tc = x2d.dtype == torch.bfloat16 and x2d.stride(0) % 8 == 0 and x2d.data_ptr() % 16 == 0
+        use_tc = (x2d.dtype == torch.bfloat16 and x2d.stride(0) % 8 == 0 and x2d.data_ptr() % 16 == 0) or ops.f32_tc_ok(x4)
         ops.conv2d(x4, self.pk, y4, act=self.act, use_tc=use_tc)
         return y2d

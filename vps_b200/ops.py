@@ -138,6 +138,7 @@ class PackedConv:
         self.scale = scale.contiguous().float() if scale is not None else None
         self.bias = bias.contiguous().float() if bias is not None else None
         self._tc = {}
+        self._tc32 = None
         self._simt = None
 
     def gran(self):
@@ -155,6 +156,12 @@ class PackedConv:
             self._tc[gran] = buf
         return self._tc[gran]
 
+    def tc32(self):
+        """[tf32 | bf16 | bf16] planes of the fp32-parity tensor-core kernel (vps_conv2d_tc32)."""
+        if self._tc32 is None:
+            self._tc32 = pack_tc32([self])
+        return self._tc32
+
     def simt(self):
         if self._simt is None:
             buf = torch.empty(self.kh * self.kw * self.cin * self.cout, dtype=torch.float32,
@@ -165,6 +172,31 @@ class PackedConv:
             torch.cuda.current_stream().synchronize()   # one-time: see tc()
             self._simt = buf
         return self._simt
+
+
+def pack_tc32(pws):
+    """one packed tc32 weight buffer for len(pws) problems of identical geometry (the stride phases of a transposed
+    convolution share a launch and therefore a buffer)."""
+    p0 = pws[0]
+    n = len(pws)
+    nbytes = lib().vps_packed_tc32_bytes(p0.cout, p0.cin, p0.kh, p0.kw, n)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=p0.weight.device)
+    for i, pw in enumerate(pws):
+        assert (pw.cout, pw.cin, pw.kh, pw.kw) == (p0.cout, p0.cin, p0.kh, p0.kw)
+        check(lib().vps_pack_weights_tc32(_ptr(pw.weight), _ptr(pw.scale), _ptr(buf), pw.cout, pw.cin, pw.kh, pw.kw,
+                                          int(pw.transposed), i, n, stream()), "pack_weights_tc32")
+    torch.cuda.current_stream().synchronize()   # one-time: the packed buffer may next be read from ANY stream / branch
+    return buf
+
+
+# fp32 activations: True = tensor cores with split operands (vps_conv2d_tc32, the "tc32" parity precision),
+# False = CUDA-core fp32 FMA (vps_conv2d_simt, the debugging reference of the parity mode)
+F32_TC = [False]
+
+
+def f32_tc_ok(x):
+    """fp32 activations the tc32 kernel can read through TMA: 16-byte aligned base and pixel stride"""
+    return F32_TC[0] and x.dtype == torch.float32 and vt(x).cs % 4 == 0 and x.data_ptr() % 16 == 0
 
 
 def _conv_args(x, pw, y, stride, pad, act, slope, res, res_after_act, out_scale, oh, ow, omap, pad_hw):
@@ -194,7 +226,10 @@ def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_aft
     if PROFILE is not None:
         _NOTE["flops"] = 2 * x.shape[0] * a.oh * a.ow * pw.cout * pw.cin * a.kh * a.kw
         _NOTE["tag"] = "%dx%d s%d %d->%d @%dx%d" % (a.kh, a.kw, a.sh, pw.cin, pw.cout, a.oh, a.ow)
-    if use_tc:
+    if use_tc and x.dtype == torch.float32:
+        a.w = pw.tc32().data_ptr()
+        check(lib().vps_conv2d_tc32(C.byref(a), stream()), "conv2d_tc32")
+    elif use_tc:
         a.cin_gran = pw.gran()
         a.w = pw.tc().data_ptr()
         check(lib().vps_conv2d_tc(C.byref(a), stream()), "conv2d_tc")
@@ -204,21 +239,25 @@ def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_aft
     return y
 
 
-def conv2d_tc_multi(x, pws, y, pads, omaps, act=ACT_NONE, slope=0.1, out_scale=1.0, oh=None, ow=None):
+def conv2d_tc_multi(x, pws, y, pads, omaps, act=ACT_NONE, slope=0.1, out_scale=1.0, oh=None, ow=None, shared32=None):
     """Up to 4 sub-convolutions (same input / output tensors, stride 1) in one persistent tensor-core launch:
-    the stride phases of a transposed convolution."""
+    the stride phases of a transposed convolution.  fp32 x: `shared32` = pack_tc32(pws)."""
     n = len(pws)
     arr = (VpsConvArgs * n)()
     gran = pws[0].gran()
+    f32 = x.dtype == torch.float32
     for i in range(n):
         a = _conv_args(x, pws[i], y, 1, 0, act, slope, None, False, out_scale, oh, ow, omaps[i], pads[i])
         a.cin_gran = gran
-        a.w = pws[i].tc(gran).data_ptr()
+        a.w = shared32.data_ptr() if f32 else pws[i].tc(gran).data_ptr()
         arr[i] = a
     if PROFILE is not None:
         _NOTE["flops"] = 2 * x.shape[0] * arr[0].oh * arr[0].ow * pws[0].cout * pws[0].cin * arr[0].kh * arr[0].kw * n
         _NOTE["tag"] = "%dx%d x%d phases %d->%d @%dx%d" % (arr[0].kh, arr[0].kw, n, pws[0].cin, pws[0].cout, arr[0].oh, arr[0].ow)
-    check(lib().vps_conv2d_tc_multi(arr, n, stream()), "conv2d_tc_multi")
+    if f32:
+        check(lib().vps_conv2d_tc32_multi(arr, n, stream()), "conv2d_tc32_multi")
+    else:
+        check(lib().vps_conv2d_tc_multi(arr, n, stream()), "conv2d_tc_multi")
     return y
 
 
