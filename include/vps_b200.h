@@ -102,16 +102,20 @@ int64_t vps_packed_tc_bytes(int cout, int cin, int kh, int kw, int cin_gran);
 /* ---- fp32-parity tensor-core convolution ("tc32" precision) ------------------------------------
  * Same contract as vps_conv2d_tc, but x (and y, res) are fp32: the reference's convolutions are fp32 cuDNN calls
  * (resnet.py:506-517, flownet2.py:133-198, fpn.py:100-139 ...) and north_star asks for label maps / ids bit-exact.
- * Each operand is split on the fly into tf32(v) + bf16 corrections and three tcgen05 products
- *   tf32(a)*tf32(b) + bf16(a - tf32(a))*bf16(b) + bf16(a)*bf16(b - tf32(b))
- * accumulate in fp32 TMEM (~2^-21 relative per product; 4 bf16-equivalent MMA passes).  Weights are pre-split by
- * vps_pack_weights_tc32 into [tf32 | bf16 | bf16] planes; the nprob stride phases of a transposed convolution share
- * ONE packed buffer (args[i].w identical, problem i = plane slice i). */
+ * Each operand is split on the fly into fp16(v) + bf16 corrections and three tcgen05 products
+ *   fp16(a)*fp16(b) + bf16(a - fp16(a))*bf16(b) + bf16(a)*bf16(b - fp16(b))
+ * are summed (~2^-21 relative per product, 3 tensor-core passes).  Because tcgen05.mma truncates when it adds into its
+ * accumulator, the main product is accumulated in short chains that are promoted to round-to-nearest register sums
+ * (conv_tc32.cu).  Weights are pre-split by vps_pack_weights_tc32 into [fp16 | bf16 | bf16] planes; the nprob stride
+ * phases of a transposed convolution share ONE packed buffer (args[i].w identical, problem i = plane slice i).
+ * |value| > 65504 in x or w saturates the fp16 plane (the result then carries ~8 correct bits) and is counted:
+ * vps_tc32_overflow(reset) returns the count (device sync) -- callers must treat non-zero as an error. */
 int vps_conv2d_tc32(const vps_conv_args* a, void* stream);
 int vps_conv2d_tc32_multi(const vps_conv_args* a, int nprob, void* stream);
 int vps_pack_weights_tc32(const float* w_oihw, const float* scale, void* dst, int cout, int cin, int kh, int kw,
                           int transposed, int prob, int nprob, void* stream);
 int64_t vps_packed_tc32_bytes(int cout, int cin, int kh, int kw, int nprob);
+int vps_tc32_overflow(int reset);
 
 /* explicit im2col for small-cin layers feeding vps_conv2d_tc as a 1x1 conv: cols is NHWC
  * [n, oh, ow, kpad] with k = (r*kw+s)*cin + ci, zero padded to cols.c. */

@@ -39,6 +39,10 @@ def split(x, p):
     if p == 11:
         h = x.bfloat16().float()
         return [h, (x - h).half().float()]
+    if p == 13:      # the scheme of vps_conv2d_tc32: A = fp16(x), A2 = fp16(2^11 (x - A)); products A*B + 2^-11 (A2*B + A*B2)
+        t = x.half().float()
+        assert torch.isfinite(t).all(), "fp16 overflow"
+        return [t, ((x - t) * 2048.0).half().float() / 2048.0]
     if p == 12:      # fp16 main (11 bits, limited range) + bf16 corrections
         global MAXABS, MINNZ
         MAXABS = max(MAXABS, float(x.abs().max()))
@@ -60,6 +64,8 @@ def pairs(p):
         return [(0, 0), (0, 1), (1, 0), (1, 1)]
     if p == 12:
         return [(0, 0), (1, 2), (2, 1)]
+    if p == 13:
+        return [(0, 0), (1, 0), (0, 1)]
     return [(i, j) for i in range(p) for j in range(p) if i + j < p]
 
 

@@ -9,7 +9,7 @@ from vps_b200.layers import empty_nhwc
 
 dev = torch.device("cuda:0")
 ops.F32_TC[0] = True
-print("GROUP", os.environ.get("VPS_TC32_GROUP"), "NEG", os.environ.get("VPS_TC32_NEG"))
+print("GROUP", os.environ.get("VPS_TC32_GROUP"))
 for name, fx, fw in (("zero-mean", lambda t: t, lambda t: t), ("positive", lambda t: t.abs(), lambda t: t.abs()),
                      ("x>=0, w mixed", lambda t: t.abs(), lambda t: t)):
     g = torch.Generator().manual_seed(3)

@@ -3,31 +3,38 @@
 // The reference computes every convolution in fp32 (cuDNN, e.g. resnet.py:506-517, flownet2.py:133-198) and
 // north_star asks for label maps / track ids bit-exact and logits within 1e-3 of it -- which a single bf16 pass
 // (8 significant bits per operand) cannot give.  This kernel keeps activations and results fp32 in HBM and feeds the
-// tensor cores three products per K slab that together carry ~21 significant bits of every operand:
+// tensor cores three fp16 products per K slab that together carry ~23 significant bits of every operand:
 //
-//     a = A + a_lo,  A = tf32(a) (round to nearest, 11 significant bits),  b = B + b_lo likewise
-//     a*b ~= A*B  [kind::tf32]  +  bf16(a_lo)*bf16(b)  [kind::f16]  +  bf16(a)*bf16(b_lo)  [kind::f16]
+//     a = A + 2^-11 * A2,   A = fp16(a) (round to nearest),  A2 = fp16(2^11 * (a - A))      [b = B + 2^-11 * B2 likewise]
+//     a*b ~= A*B  +  2^-11 * (A2*B + A*B2)                      (all kind::f16, f16 x f16, fp32 accumulate)
 //
-// (dropped: a_lo*b_lo ~ 2^-24, and the bf16 rounding of the two correction products ~ 2^-21 each), all accumulated
-// into the same fp32 TMEM accumulator.  Cost: 2 (tf32 runs at half the bf16 rate) + 1 + 1 = 4 bf16-equivalent MMA
-// passes instead of the 6 a three-way bf16 split (bf16x6/"bf16x9"-style) needs for the same accuracy class; the
-// CPU emulation of this arithmetic through the whole FuseTrack path (tools/emulate_split.py) reproduces the fp32
-// oracle's label maps / ids / proposals bit-exactly, which a two-way bf16 split (bf16x3) does not.
+// a - A is exact in fp32 and at most half an fp16 ulp of a, so 2^11 * (a - A) never exceeds |a| (no overflow) and stays
+// a normal fp16 number whenever a is one; dropped are a_lo*b_lo <= 2^-24 |ab| and the fp16 rounding of A2 / B2 (2^-23).
+// Cost: 3 tensor-core passes -- against 6 for a three-way bf16 split of the same accuracy class; a two-way bf16 split
+// (bf16x3) is NOT enough: its CPU emulation through the whole FuseTrack path (tools/emulate_split.py) flips proposals /
+// ids / label pixels.  fp16's narrow exponent range is harmless below (values under 2^-14 are carried by A2: the residual
+// of a subnormal A is <= 2^-25, i.e. 2^-14 after scaling); values above 65504 are saturated and counted in a device
+// flag the caller must check (vps_tc32_overflow) -- the result then only has fp16-saturation accuracy.
 //
-// Pipeline per CTA (persistent, one 128-pixel x block_n tile at a time, K consumed 32 channels per step):
-//   warp 0     : TMA producer.  Activation boxes arrive as raw fp32 {32 ch, pixels} (SWIZZLE_128B rows of 128 B); weights
-//                come pre-split from vps_pack_weights_tc32 (tf32 plane + two bf16 planes) through their own ring.
-//   warps 6-9  : converters.  Rewrite the fp32 box IN PLACE as tf32(a) and emit the two bf16 planes bf16(a - tf32(a)),
-//                bf16(a) as SWIZZLE_64B operand tiles next to it (generic-proxy writes -> fence.proxy.async -> mbarrier).
-//                In halo mode (stride 1, > 1 tap) one converted (th+kh-1) x (tw+kw-1) box feeds all kh*kw taps.
-//   warp 1     : MMA issuer: per (tap, 32-channel chunk) 4 x tcgen05.mma.kind::tf32 (K = 8) + 2 x 2 x kind::f16 (K = 16).
-//   warps 8-15 : promotion + epilogue.  tcgen05.mma adds into its fp32 accumulator with TRUNCATION (measured here: the
-//                error of a K-long chain grows like (#MMAs) * 2^-24, biased towards zero -- 1.3e-4 after 2300 MMAs), so a
-//                chain is cut into groups of `group` K steps: the MMA warp starts every group on a fresh TMEM buffer
-//                (accumulate = 0, buffers ping-pong), these warps drain finished groups with tcgen05.ld and keep the running
-//                sum in registers with round-to-nearest fp32 adds (the classic fix for emulated-fp32 tensor-core GEMMs),
-//                then apply bias / activation / residual and store.  setmaxnreg moves registers from the producer /
-//                converter warpgroups to these two (128 running sums per thread for a 256-wide tile).
+// tcgen05.mma adds into its fp32 accumulator with TRUNCATION towards zero (measured: tools/probe_tc_rounding.py -- a chain
+// of m MMAs on same-sign data loses 0.34*m ulp, 1.3e-4 relative after 2300 MMAs; negating A gives the bit-identical
+// mirrored result, i.e. sign-magnitude RZ).  A bias that compounds over ~60 stacked layers, so:
+//   * the large main product accumulates in chains of only `group` K steps (2 MMAs each) on ping-pong TMEM buffers that
+//     start from accumulate = 0; finished groups are promoted to per-thread register sums with round-to-nearest fp32 adds;
+//   * the two correction products accumulate (un-scaled: A2*B + A*B2) for the whole tile in their own TMEM buffer and
+//     are added once at the end with one fused multiply-add by 2^-11 per element.
+//
+// Pipeline per CTA (persistent, one 128-pixel x block_n (<= 128) tile at a time, K consumed 32 channels per step):
+//   warp 0     : TMA producer: raw fp32 activation boxes {32 ch, pixels} into a staging ring; pre-split weight tiles
+//                [B | B2] (vps_pack_weights_tc32) into the B ring.
+//   warps 2-7  : converters: staging box -> two SWIZZLE_64B operand planes A, A2
+//                (generic-proxy writes -> fence.proxy.async -> mbarrier).  In halo mode (stride 1, > 1 tap) one converted
+//                (th+kh-1) x (tw+kw-1) box feeds all kh*kw taps through shifted descriptor start addresses.
+//   warp 1     : MMA issuer: 6 x tcgen05.mma.kind::f16 (M128 x N x K16) per (tap, 32-channel chunk).
+//   warps 8-15 : promotion + epilogue: tcgen05.ld finished groups, RN-add into registers (setmaxnreg gives these two
+//                warpgroups 200 registers), finally bias / activation / residual and the NHWC store (conv_tc.cu's epilogue).
+#include <cuda_fp16.h>
+
 #include "conv_tc_common.cuh"
 
 namespace {
@@ -35,32 +42,42 @@ namespace {
 constexpr int T32_EPI_WARPS = 8;            // warps 8..15: two per TMEM lane quarter, alternating 32-column chunks
 constexpr int T32_CONV_WARPS = 6;           // warps 2..7
 constexpr int T32_THREADS = 64 + 32 * (T32_EPI_WARPS + T32_CONV_WARPS);     // 512 = 4 warpgroups
-constexpr int T32_MAX_BUF = 4;              // TMEM accumulator buffers (512 columns / block_n, at most 4)
 constexpr int T32_REGS_LOW = 56, T32_REGS_HIGH = 200;    // setmaxnreg: 256 * 56 + 256 * 200 = 65536
-constexpr int T32_KC = 32;                 // channels per K step: 128-byte tf32 rows, 64-byte bf16 rows
+constexpr int T32_KC = 32;                  // channels per K step: 64-byte operand rows (SWIZZLE_64B), 2 x K16
+constexpr int T32_MAX_N = 128;              // TMEM: 2 main (ping-pong groups) + 2 correction (per tile) buffers of 128 columns
+constexpr int T32_STAGE_SLOTS = 2;          // fp32 staging boxes (TMA -> converters)
+constexpr int T32_PLANES = 2;               // operand planes: fp16(v), fp16(2^11 (v - fp16(v)))
+constexpr float T32_LO_SCALE = 2048.f, T32_LO_INV = 1.f / 2048.f;
+
+__device__ unsigned int g_tc32_overflow = 0;     // activations / weights that exceeded the fp16 range of the main product
 
 struct Tc32Extra {
   int rows;                  // activation rows (pixels) per A item: halo_h * halo_w, or 128
-  int a_l_off, a_h_off;      // byte offsets of the two bf16 planes inside an A ring slot
-  int b_half_bytes;          // block_n * 128: one B ring slot holds either the tf32 weight tile or the two bf16 tiles
-  int nk8_last, nk16_last;   // K8 / K16 slabs of the last channel chunk that hold real channels
-  int group;                 // K steps accumulated inside the tensor core before the sum is promoted to registers
-  int alt_neg;               // 1: odd groups accumulate -A*B (instruction-descriptor negate bit) and are subtracted
-  int nbuf, buf_cols;        // TMEM accumulator buffers and their column pitch
+  int plane_bytes;           // bytes of one operand plane of an A item (rows * 64, padded to 1024)
+  int stage_bytes;           // bytes of one fp32 staging slot (rows * 128, padded to 1024)
+  int b_plane_bytes;         // block_n * 64: one weight plane of one step
+  int nk_last;               // K16 slabs of the last channel chunk that hold real channels
+  int group;                 // K steps of the main product accumulated inside the tensor core before promotion
 };
 
 struct Ring32 {
-  uint32_t a_base, a_stage_bytes, b_base, b_stage_bytes, bar_base;
-  __device__ __forceinline__ uint32_t afull(int s) const { return bar_base + 8u * s; }
-  __device__ __forceinline__ uint32_t aconv(int s) const { return bar_base + 8u * (MAX_STAGES + s); }
-  __device__ __forceinline__ uint32_t aempty(int s) const { return bar_base + 8u * (2 * MAX_STAGES + s); }
-  __device__ __forceinline__ uint32_t bfull(int s) const { return bar_base + 8u * (3 * MAX_STAGES + s); }
-  __device__ __forceinline__ uint32_t bempty(int s) const { return bar_base + 8u * (4 * MAX_STAGES + s); }
-  __device__ __forceinline__ uint32_t gfull(int a) const { return bar_base + 8u * (5 * MAX_STAGES + a); }
-  __device__ __forceinline__ uint32_t gempty(int a) const { return bar_base + 8u * (5 * MAX_STAGES + T32_MAX_BUF + a); }
-  __device__ __forceinline__ uint32_t tmem_slot() const { return bar_base + 8u * (5 * MAX_STAGES + 2 * T32_MAX_BUF); }
+  uint32_t s_base, s_bytes;      // staging ring
+  uint32_t a_base, a_bytes;      // operand-plane ring (T32_PLANES planes per slot)
+  uint32_t b_base, b_bytes;      // weight ring (T32_PLANES planes per slot)
+  uint32_t bar_base;
+  __device__ __forceinline__ uint32_t sfull(int s) const { return bar_base + 8u * s; }
+  __device__ __forceinline__ uint32_t sempty(int s) const { return bar_base + 8u * (MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t pfull(int s) const { return bar_base + 8u * (2 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t pempty(int s) const { return bar_base + 8u * (3 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t bfull(int s) const { return bar_base + 8u * (4 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t bempty(int s) const { return bar_base + 8u * (5 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t gfull(int a) const { return bar_base + 8u * (6 * MAX_STAGES + a); }
+  __device__ __forceinline__ uint32_t gempty(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 2 + a); }
+  __device__ __forceinline__ uint32_t cfull(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 4 + a); }
+  __device__ __forceinline__ uint32_t cempty(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 6 + a); }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar_base + 8u * (6 * MAX_STAGES + 8); }
 };
-constexpr int T32_NBAR = 5 * MAX_STAGES + 2 * T32_MAX_BUF;
+constexpr int T32_NBAR = 6 * MAX_STAGES + 8;
 constexpr int T32_BAR_BYTES = 8 * (T32_NBAR + 2);
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3,
@@ -71,36 +88,24 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major operand tile descriptor: layout 2 = SWIZZLE_128B (128-byte rows), 4 = SWIZZLE_64B (64-byte rows)
-__device__ __forceinline__ uint64_t desc_hi(uint32_t layout, uint32_t sbo) {
+// K-major operand tile of 64-byte rows, SWIZZLE_64B (layout type 4): 8-row groups `sbo` bytes apart
+__device__ __forceinline__ uint64_t desc_hi64(uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
+  d |= (uint64_t)4 << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t cvt_tf32(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return u;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {     // lo -> bits [0,16)
-  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&b);
+// fp16 (round to nearest, saturating) of v; `over` collects |v| > 65504 (and NaN)
+__device__ __forceinline__ float to_f16_sat(float v, unsigned short& bits, bool& over) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  bits = h;
+  over = over || !(fabsf(v) <= 65504.f);
+  return __half2float(__ushort_as_half(h));
 }
 
-// ---------------------------------------------------------------- tile walk shared by all roles
+// ---------------------------------------------------------------- tile walk shared by the roles
 struct TileCoord {
   int prob, n_idx, img, ty, tx;
 };
@@ -120,13 +125,13 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, int tile)
 
 // ---------------------------------------------------------------- warp 0: TMA producer
 __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, const CUtensorMap* tmA,
-                                           const CUtensorMap* tmBt, const CUtensorMap* tmBhl) {
+                                           const CUtensorMap* tmB) {
   const int ntaps = p.kh * p.kw, kw = p.kw;
   const bool halo = p.halo != 0;
-  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes, bhalf = (uint32_t)e.b_half_bytes;
+  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes, b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
   const int bn = p.block_n;
-  int as = 0, bs = 0;
-  uint32_t aphase = 0, bphase = 0;
+  int ss = 0, bs = 0;
+  uint32_t sphase = 0, bphase = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = tile_coord(p, tile);
     const int x_base = t.tx * p.tw * p.sw - p.pw_[t.prob];
@@ -136,25 +141,18 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
       int r = 0, s = 0;
       for (int tap = 0; tap < ntaps; ++tap) {
         if (!halo || tap == 0) {
-          mbar_wait(rg.aempty(as), aphase ^ 1);
+          mbar_wait(rg.sempty(ss), sphase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(rg.afull(as), a_box_bytes);
-            tma_load_4d(rg.a_base + as * rg.a_stage_bytes, tmA, rg.afull(as), cc * T32_KC, halo ? x_base : x_base + s,
+            mbar_expect_tx(rg.sfull(ss), a_box_bytes);
+            tma_load_4d(rg.s_base + ss * rg.s_bytes, tmA, rg.sfull(ss), cc * T32_KC, halo ? x_base : x_base + s,
                         halo ? y_base : y_base + r, t.img);
           }
-          if (++as == p.a_stages) { as = 0; aphase ^= 1; }
+          if (++ss == T32_STAGE_SLOTS) { ss = 0; sphase ^= 1; }
         }
-        // weight tiles of this (tap, chunk): slot 0 = tf32 plane, slot 1 = the two bf16 planes
         mbar_wait(rg.bempty(bs), bphase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(rg.bfull(bs), bhalf);
-          tma_load_4d(rg.b_base + bs * rg.b_stage_bytes, tmBt, rg.bfull(bs), cc * T32_KC, n0, tap, t.prob);
-        }
-        if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
-        mbar_wait(rg.bempty(bs), bphase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(rg.bfull(bs), bhalf);
-          tma_load_5d(rg.b_base + bs * rg.b_stage_bytes, tmBhl, rg.bfull(bs), cc * T32_KC, n0, tap, t.prob, 0);
+        if (elect_one()) {     // both weight planes of this (tap, chunk) in one 5-D box
+          mbar_expect_tx(rg.bfull(bs), b_bytes);
+          tma_load_5d(rg.b_base + bs * rg.b_bytes, tmB, rg.bfull(bs), cc * T32_KC, n0, tap, t.prob, 0);
         }
         if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
         if (++s == kw) { s = 0; ++r; }
@@ -163,139 +161,133 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
   }
 }
 
-// ---------------------------------------------------------------- warps 6..9: fp32 box -> tf32 (in place) + two bf16 planes
+// ---------------------------------------------------------------- warps 2..7: fp32 box -> fp16 / bf16 / bf16 operand planes
 __device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, int ctid) {
   const int ntaps = p.kh * p.kw;
   const int items_per_tile = p.cin_chunks * (p.halo ? 1 : ntaps);
   const int tasks = e.rows * 4;                       // 8 channels (two 16-byte fp32 chunks) per task
-  int as = 0;
-  uint32_t aphase = 0;
+  int ss = 0, as = 0;
+  uint32_t sphase = 0, aphase = 0;
+  bool over = false;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     for (int it = 0; it < items_per_tile; ++it) {
-      mbar_wait(rg.afull(as), aphase);
-      const uint32_t slot = rg.a_base + as * rg.a_stage_bytes;
+      mbar_wait(rg.sfull(ss), sphase);
+      mbar_wait(rg.pempty(as), aphase ^ 1);
+      const uint32_t src = rg.s_base + ss * rg.s_bytes;
+      const uint32_t dst = rg.a_base + as * rg.a_bytes;
       for (int task = ctid; task < tasks; task += 32 * T32_CONV_WARPS) {
         const int r = task >> 2, j = task & 3;
-        const uint32_t row_t = slot + (uint32_t)r * 128u;
+        // staging rows are 128 bytes, SWIZZLE_128B (written by TMA): 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+        const uint32_t row_s = src + (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        const uint32_t p0 = row_t + (((uint32_t)(2 * j) ^ sw) << 4), p1 = row_t + (((uint32_t)(2 * j + 1) ^ sw) << 4);
         float v[8];
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(p0));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(p1));
-        uint32_t t[8];
-        float lo[8];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                     : "r"(row_s + (((uint32_t)(2 * j) ^ sw) << 4)));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "r"(row_s + (((uint32_t)(2 * j + 1) ^ sw) << 4)));
+        unsigned short hb[8], lb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          t[q] = cvt_tf32(v[q]);
-          lo[q] = v[q] - __uint_as_float(t[q]);       // exact: both share the exponent range, <= 13 significant bits
+          const float lo = v[q] - to_f16_sat(v[q], hb[q], over);     // exact in fp32, |lo| <= half an fp16 ulp of v
+          bool dummy = false;
+          to_f16_sat(lo * T32_LO_SCALE, lb[q], dummy);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p0), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p1), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]) : "memory");
-        // bf16 planes: 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
-        const uint32_t off64 = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
-        const uint32_t pl = slot + (uint32_t)e.a_l_off + off64, ph = slot + (uint32_t)e.a_h_off + off64;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"(pack_bf16(lo[0], lo[1])), "r"(pack_bf16(lo[2], lo[3])),
-                     "r"(pack_bf16(lo[4], lo[5])), "r"(pack_bf16(lo[6], lo[7])) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ph), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
-                     "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
+        // operand planes: 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
+        const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
+        const uint32_t pm = dst + off, pl = pm + (uint32_t)e.plane_bytes;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"((uint32_t)hb[0] | ((uint32_t)hb[1] << 16)),
+                     "r"((uint32_t)hb[2] | ((uint32_t)hb[3] << 16)), "r"((uint32_t)hb[4] | ((uint32_t)hb[5] << 16)),
+                     "r"((uint32_t)hb[6] | ((uint32_t)hb[7] << 16)) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"((uint32_t)lb[0] | ((uint32_t)lb[1] << 16)),
+                     "r"((uint32_t)lb[2] | ((uint32_t)lb[3] << 16)), "r"((uint32_t)lb[4] | ((uint32_t)lb[5] << 16)),
+                     "r"((uint32_t)lb[6] | ((uint32_t)lb[7] << 16)) : "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
-      mbar_arrive(rg.aconv(as));
+      mbar_arrive(rg.sempty(ss));                                        // staging slot may be refilled
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> tensor-core reads
+      mbar_arrive(rg.pfull(as));
+      if (++ss == T32_STAGE_SLOTS) { ss = 0; sphase ^= 1; }
       if (++as == p.a_stages) { as = 0; aphase ^= 1; }
     }
   }
+  if (over) atomicAdd(&g_tc32_overflow, 1u);
 }
 
 // ---------------------------------------------------------------- warp 1: MMA issuer
 __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base) {
   const uint32_t nfield = ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-  const uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | nfield;     // D = f32, A = B = tf32, K-major
-  const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | nfield;     // D = f32, A = B = bf16
+  const uint32_t idesc = (1u << 4) | nfield;                              // D = f32, A = B = f16, K-major
   const int ntaps = p.kh * p.kw, kw = p.kw;
   const bool halo = p.halo != 0;
   const uint32_t hw = (uint32_t)p.halo_w;
-  const uint64_t a_hi_t = desc_hi(2, halo ? hw * 128u : 1024u), b_hi_t = desc_hi(2, 1024u);
-  const uint64_t a_hi_h = desc_hi(4, halo ? hw * 64u : 512u), b_hi_h = desc_hi(4, 512u);
-  const uint32_t b_l_off = (uint32_t)p.block_n * 64u;       // second bf16 weight plane inside its B slot
-  int as = 0, bs = 0, gb = 0;
-  uint32_t aphase = 0, bphase = 0, gphase = 0;       // gphase: one parity bit per TMEM buffer
+  const uint64_t a_hi = desc_hi64(halo ? hw * 64u : 512u), b_hi = desc_hi64(512u);
+  const uint32_t a_plane = (uint32_t)e.plane_bytes, b_plane = (uint32_t)e.b_plane_bytes;
+  int as = 0, bs = 0, gb = 0, cb = 0;
+  uint32_t aphase = 0, bphase = 0, gphase = 0, cphase = 0;       // gphase / cphase: one parity bit per TMEM buffer
   const int G = e.group, total_steps = p.cin_chunks * ntaps;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    int step = 0, in_group = 0, gidx = 0;
-    uint32_t d_tmem = 0, first = 0, neg = 0;
+    int step = 0, in_group = 0;
+    uint32_t d_main = 0, first = 0, cfirst = 0;
+    // the correction buffer of this tile must have been drained by the promotion warps
+    mbar_wait(rg.cempty(cb), ((cphase >> cb) & 1u) ^ 1u);
+    const uint32_t d_corr = tmem_base + (uint32_t)(2 * T32_MAX_N + cb * T32_MAX_N);
     for (int cc = 0; cc < p.cin_chunks; ++cc) {
-      const bool last = cc == p.cin_chunks - 1;
-      const int nk8 = last ? e.nk8_last : 4, nk16 = last ? e.nk16_last : 2;
+      const int nk16 = cc == p.cin_chunks - 1 ? e.nk_last : 2;
       int r = 0, s = 0, a_cur = 0;
       uint32_t a_slot = 0;
       for (int tap = 0; tap < ntaps; ++tap) {
-        if (in_group == 0) {           // a new accumulation group starts on a drained TMEM buffer with accumulate = 0
+        if (in_group == 0) {           // a new group of the main product starts on a drained buffer with accumulate = 0
           mbar_wait(rg.gempty(gb), ((gphase >> gb) & 1u) ^ 1u);
-          tc_fence_after();
-          d_tmem = tmem_base + (uint32_t)(gb * e.buf_cols);
+          d_main = tmem_base + (uint32_t)(gb * T32_MAX_N);
           first = 0;
-          neg = (e.alt_neg && (gidx & 1)) ? (1u << 13) : 0u;
-          ++gidx;
         }
         if (!halo || tap == 0) {
-          mbar_wait(rg.aconv(as), aphase);
+          mbar_wait(rg.pfull(as), aphase);
           a_cur = as;
-          a_slot = rg.a_base + as * rg.a_stage_bytes;
+          a_slot = rg.a_base + as * rg.a_bytes;
           if (++as == p.a_stages) { as = 0; aphase ^= 1; }
         }
-        const uint32_t shift = halo ? (uint32_t)(r * (int)hw + s) : 0u;
-        const uint32_t a_t = a_slot + shift * 128u;
-        const uint32_t a_l = a_slot + (uint32_t)e.a_l_off + shift * 64u, a_h = a_slot + (uint32_t)e.a_h_off + shift * 64u;
-        // ---- tf32 x tf32
-        mbar_wait(rg.bfull(bs), bphase);
-        tc_fence_after();
-        {
-          const uint32_t b_t = rg.b_base + bs * rg.b_stage_bytes;
-          if (elect_one()) {
-            const uint64_t ad = a_hi_t | (uint64_t)((a_t & 0x3FFFF) >> 4), bd = b_hi_t | (uint64_t)((b_t & 0x3FFFF) >> 4);
-            umma_tf32(d_tmem, ad, bd, idesc_tf32 | neg, first);
-            if (nk8 > 1) umma_tf32(d_tmem, ad + 2, bd + 2, idesc_tf32 | neg, 1u);
-            if (nk8 > 2) umma_tf32(d_tmem, ad + 4, bd + 4, idesc_tf32 | neg, 1u);
-            if (nk8 > 3) umma_tf32(d_tmem, ad + 6, bd + 6, idesc_tf32 | neg, 1u);
-            umma_commit(rg.bempty(bs));
-          }
-        }
-        first = 1;
-        if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
-        // ---- bf16(a_lo) x bf16(b)  +  bf16(a) x bf16(b_lo)
         mbar_wait(rg.bfull(bs), bphase);
         tc_fence_after();
         ++step;
         const bool close = (++in_group == G) || step == total_steps;
         {
-          const uint32_t b_h = rg.b_base + bs * rg.b_stage_bytes, b_l = b_h + b_l_off;
+          const uint32_t shift = halo ? (uint32_t)(r * (int)hw + s) * 64u : 0u;
+          const uint32_t a_m = a_slot + shift, b_m = rg.b_base + bs * rg.b_bytes;
           if (elect_one()) {
-            const uint64_t ald = a_hi_h | (uint64_t)((a_l & 0x3FFFF) >> 4), ahd = a_hi_h | (uint64_t)((a_h & 0x3FFFF) >> 4);
-            const uint64_t bhd = b_hi_h | (uint64_t)((b_h & 0x3FFFF) >> 4), bld = b_hi_h | (uint64_t)((b_l & 0x3FFFF) >> 4);
-            umma_bf16(d_tmem, ald, bhd, idesc_bf16 | neg, 1u);
-            if (nk16 > 1) umma_bf16(d_tmem, ald + 2, bhd + 2, idesc_bf16 | neg, 1u);
-            umma_bf16(d_tmem, ahd, bld, idesc_bf16 | neg, 1u);
-            if (nk16 > 1) umma_bf16(d_tmem, ahd + 2, bld + 2, idesc_bf16 | neg, 1u);
+            const uint64_t am = a_hi | (uint64_t)((a_m & 0x3FFFF) >> 4), al = a_hi | (uint64_t)(((a_m + a_plane) & 0x3FFFF) >> 4);
+            const uint64_t bm = b_hi | (uint64_t)((b_m & 0x3FFFF) >> 4), bl = b_hi | (uint64_t)(((b_m + b_plane) & 0x3FFFF) >> 4);
+            // main: A x B -> group buffer
+            umma_bf16(d_main, am, bm, idesc, first);
+            if (nk16 > 1) umma_bf16(d_main, am + 2, bm + 2, idesc, 1u);
+            // corrections: A2 x B + A x B2 -> the tile's correction buffer (scaled by 2^-11 when it is added)
+            umma_bf16(d_corr, al, bm, idesc, cfirst);
+            if (nk16 > 1) umma_bf16(d_corr, al + 2, bm + 2, idesc, 1u);
+            umma_bf16(d_corr, am, bl, idesc, 1u);
+            if (nk16 > 1) umma_bf16(d_corr, am + 2, bl + 2, idesc, 1u);
             umma_commit(rg.bempty(bs));
-            if (!halo || tap == ntaps - 1) umma_commit(rg.aempty(a_cur));
+            if (!halo || tap == ntaps - 1) umma_commit(rg.pempty(a_cur));
             if (close) umma_commit(rg.gfull(gb));
+            if (step == total_steps) umma_commit(rg.cfull(cb));
           }
         }
+        first = 1; cfirst = 1;
         if (close) {
           gphase ^= 1u << gb;
-          if (++gb == e.nbuf) gb = 0;
+          gb ^= 1;
           in_group = 0;
         }
         if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
         if (++s == kw) { s = 0; ++r; }
       }
     }
+    cphase ^= 1u << cb;
+    cb ^= 1;
   }
 }
 
 // ---------------------------------------------------------------- warps 8..15: promotion (TMEM groups -> register sums) + epilogue
 // warp -> TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter take alternate 32-column
-// chunks, so a thread owns one output pixel and up to 4 x 32 channels of running sums.
+// chunks, so a thread owns one output pixel and up to 2 x 32 channels of running sums.
 template <int ACT>
 __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base,
                                                  int warp, int lane) {
@@ -306,16 +298,17 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
   const int total_steps = p.cin_chunks * p.kh * p.kw;
   const int ngroups = (total_steps + e.group - 1) / e.group;
   const int bn = p.block_n;
-  int gb = 0;
-  uint32_t gphase = 0;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  int gb = 0, cb = 0;
+  uint32_t gphase = 0, cphase = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    float sum[4][32];
+    float sum[2][32];
     for (int g = 0; g < ngroups; ++g) {
       mbar_wait(rg.gfull(gb), (gphase >> gb) & 1u);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gb * e.buf_cols);
+      const uint32_t t_row = lane_base + (uint32_t)(gb * T32_MAX_N);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 2; ++k) {
         const int c0 = (half + 2 * k) * 32;
         if (c0 < bn) {
           uint32_t r[32];
@@ -324,9 +317,6 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
           if (g == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[k][j] = __uint_as_float(r[j]);
-          } else if (e.alt_neg && (g & 1)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[k][j] = __fsub_rn(sum[k][j], __uint_as_float(r[j]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[k][j] = __fadd_rn(sum[k][j], __uint_as_float(r[j]));
@@ -336,8 +326,29 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       tc_fence_before();
       mbar_arrive(rg.gempty(gb));
       gphase ^= 1u << gb;
-      if (++gb == e.nbuf) gb = 0;
+      gb ^= 1;
     }
+    // ---- the tile's correction products
+    mbar_wait(rg.cfull(cb), (cphase >> cb) & 1u);
+    tc_fence_after();
+    {
+      const uint32_t t_row = lane_base + (uint32_t)(2 * T32_MAX_N + cb * T32_MAX_N);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int c0 = (half + 2 * k) * 32;
+        if (c0 < bn) {
+          uint32_t r[32];
+          tmem_ld32(t_row + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[k][j] = __fmaf_rn(__uint_as_float(r[j]), T32_LO_INV, sum[k][j]);
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(rg.cempty(cb));
+    cphase ^= 1u << cb;
+    cb ^= 1;
     // ---- bias / activation / residual / store of this tile (same arithmetic as conv_tc.cu's epilogue)
     const int prob = tile / p.tiles_per_prob;
     const int t_in = tile - prob * p.tiles_per_prob;
@@ -352,7 +363,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
     const int nbase = n_idx * bn;
     const int nlim = min(p.cout, nbase + bn);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 2; ++k) {
       const int c0 = (half + 2 * k) * 32;
       if (c0 < bn && valid && nbase + c0 < nlim) {
         uint32_t r[32];
@@ -366,30 +377,30 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
 
 // ---------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(T32_THREADS, 1)
-conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBt,
-                       const __grid_constant__ CUtensorMap tmBhl, const ConvTcParams p, const Tc32Extra e) {
+conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p,
+                       const Tc32Extra e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Ring32 rg;
-  rg.a_base = smem_base; rg.a_stage_bytes = (uint32_t)p.a_stage_bytes;
-  rg.b_base = smem_base + (uint32_t)p.a_stages * rg.a_stage_bytes;
-  rg.b_stage_bytes = (uint32_t)e.b_half_bytes;
-  rg.bar_base = rg.b_base + (uint32_t)p.b_stages * rg.b_stage_bytes;
+  rg.s_base = smem_base; rg.s_bytes = (uint32_t)e.stage_bytes;
+  rg.a_base = rg.s_base + T32_STAGE_SLOTS * rg.s_bytes; rg.a_bytes = (uint32_t)T32_PLANES * (uint32_t)e.plane_bytes;
+  rg.b_base = rg.a_base + (uint32_t)p.a_stages * rg.a_bytes; rg.b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
+  rg.bar_base = rg.b_base + (uint32_t)p.b_stages * rg.b_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 2) {
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
-      if (i >= MAX_STAGES && i < 2 * MAX_STAGES) count = 32 * T32_CONV_WARPS;          // aconv: every converter thread
-      if (i >= 5 * MAX_STAGES + T32_MAX_BUF) count = 32 * T32_EPI_WARPS;              // gempty: every promotion thread
+      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;      // sempty, pfull: every converter thread
+      if ((i >= 6 * MAX_STAGES + 2 && i < 6 * MAX_STAGES + 4) || i >= 6 * MAX_STAGES + 6)
+        count = 32 * T32_EPI_WARPS;                                               // gempty, cempty: every promotion thread
       mbar_init(rg.bar_base + 8u * i, count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBt) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rg.tmem_slot()), "r"((uint32_t)TMEM_COLS)
@@ -408,7 +419,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp < 8) {
     // producer / MMA / converter warpgroups give registers away, the two promotion warpgroups take them
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T32_REGS_LOW));
-    if (warp == 0) producer32(p, e, rg, &tmA, &tmBt, &tmBhl);
+    if (warp == 0) producer32(p, e, rg, &tmA, &tmB);
     else if (warp == 1) mma32(p, e, rg, tmem_base);
     else converter32(p, e, rg, (int)threadIdx.x - 64);
   } else {
@@ -430,11 +441,12 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------- weight packing
-// planes [Bt fp32 (tf32-rounded) | Bh bf16 = bf16(w) | Bl bf16 = bf16(w - tf32(w))], each [nprob][cout_pad][tap][cin_pad]
-__global__ void pack_weights_tc32_kernel(const float* __restrict__ src, const float* __restrict__ scale, float* __restrict__ bt,
-                                         __nv_bfloat16* __restrict__ bh, __nv_bfloat16* __restrict__ bl, int cout, int cin, int kh,
-                                         int kw, int cout_pad, int cin_pad, int transposed) {
+// two planes of fp16 words, each [nprob][cout_pad][tap][cin_pad]:  B = fp16(w),  B2 = fp16(2^11 * (w - B))
+__global__ void pack_weights_tc32_kernel(const float* __restrict__ src, const float* __restrict__ scale, unsigned short* __restrict__ bm,
+                                         unsigned short* __restrict__ bl, int cout, int cin, int kh, int kw, int cout_pad,
+                                         int cin_pad, int transposed) {
   const int64_t total = (int64_t)cout_pad * kh * kw * cin_pad;
+  bool over = false;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin_pad);
     int64_t t = i / cin_pad;
@@ -447,11 +459,14 @@ __global__ void pack_weights_tc32_kernel(const float* __restrict__ src, const fl
       v = src[si];
       if (scale) v *= scale[co];
     }
-    const float tv = __uint_as_float(cvt_tf32(v));
-    bt[i] = tv;
-    bh[i] = __float2bfloat16_rn(v);
-    bl[i] = __float2bfloat16_rn(v - tv);
+    unsigned short h, l;
+    const float m = to_f16_sat(v, h, over);
+    bool dummy = false;
+    to_f16_sat((v - m) * T32_LO_SCALE, l, dummy);
+    bm[i] = h;
+    bl[i] = l;
   }
+  if (over) atomicAdd(&g_tc32_overflow, 1u);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode32() {
@@ -476,7 +491,18 @@ inline int64_t plane_elems(int cout, int cin, int kh, int kw) {
 }  // namespace
 
 extern "C" int64_t vps_packed_tc32_bytes(int cout, int cin, int kh, int kw, int nprob) {
-  return plane_elems(cout, cin, kh, kw) * 8 * nprob;
+  return plane_elems(cout, cin, kh, kw) * 2 * T32_PLANES * nprob;
+}
+
+// number of converter / packing threads that met |value| > 65504 (or NaN) since the last reset; synchronises the device
+extern "C" int vps_tc32_overflow(int reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_tc32_overflow, sizeof(v)) != cudaSuccess) return -1;
+  if (reset && v) {
+    const unsigned int z = 0;
+    cudaMemcpyToSymbol(g_tc32_overflow, &z, sizeof(z));
+  }
+  return (int)v;
 }
 
 // problem `prob` of `nprob` (the stride phases of a transposed convolution share one packed buffer; nprob = 1 otherwise)
@@ -485,12 +511,11 @@ extern "C" int vps_pack_weights_tc32(const float* w, const float* scale, void* d
   VPS_CHECK_ARG(nprob >= 1 && nprob <= MAX_PROB && prob >= 0 && prob < nprob, "pack_weights_tc32: prob %d of %d", prob, nprob);
   const int cout_pad = (cout + 15) / 16 * 16, cin_pad = (cin + T32_KC - 1) / T32_KC * T32_KC;
   const int64_t n = plane_elems(cout, cin, kh, kw);
-  float* bt = (float*)dst + (int64_t)prob * n;
-  __nv_bfloat16* bh = (__nv_bfloat16*)((char*)dst + 4 * n * nprob) + (int64_t)prob * n;
-  __nv_bfloat16* bl = (__nv_bfloat16*)((char*)dst + 6 * n * nprob) + (int64_t)prob * n;
+  unsigned short* base = (unsigned short*)dst;
+  unsigned short* bm = base + (int64_t)prob * n;
+  unsigned short* bl = base + n * nprob + (int64_t)prob * n;
   const int blocks = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
-  pack_weights_tc32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, scale, bt, bh, bl, cout, cin, kh, kw, cout_pad, cin_pad,
-                                                                    transposed);
+  pack_weights_tc32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, scale, bm, bl, cout, cin, kh, kw, cout_pad, cin_pad, transposed);
   VPS_CUDA_LAST("pack_weights_tc32");
   return VPS_OK;
 }
@@ -543,48 +568,44 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   const int halo_h = p.th + a->kh - 1;
   e.rows = halo ? halo_h * p.halo_w : BLOCK_M;
   p.a_box_bytes = e.rows * 128;
-  e.a_l_off = (e.rows * 128 + 1023) / 1024 * 1024;
-  e.a_h_off = e.a_l_off + (e.rows * 64 + 1023) / 1024 * 1024;
-  p.a_stage_bytes = e.a_h_off + (e.rows * 64 + 1023) / 1024 * 1024;
+  e.stage_bytes = (e.rows * 128 + 1023) / 1024 * 1024;
+  e.plane_bytes = (e.rows * 64 + 1023) / 1024 * 1024;
+  p.a_stage_bytes = T32_PLANES * e.plane_bytes;
   p.tiles_x = vps::cdiv(a->ow, p.tw); p.tiles_y = vps::cdiv(a->oh, p.th);
   p.kh = a->kh; p.kw = a->kw; p.sh = a->sh; p.sw = a->sw;
   p.cin_chunks = cin_pad / T32_KC;
   const int rem = a->cin - (p.cin_chunks - 1) * T32_KC;
-  e.nk8_last = (rem + 7) / 8; e.nk16_last = (rem + 15) / 16;
+  e.nk_last = (rem + 15) / 16;
   const int ntaps = a->kh * a->kw;
   p.a_stages = halo ? 2 : 3;
   const int smem_budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64;
-  // N tile: divisor of cout_pad (multiple of 16, <= 256) minimising waves * (steps * step clocks + epilogue); a step is
-  // 8 MMAs = 4*bn clocks at the MMA floor, ~350 clocks of issue / barrier latency, or its weight bytes at the L2 rate
+  const int a_side = T32_STAGE_SLOTS * e.stage_bytes + p.a_stages * p.a_stage_bytes;
+  // N tile: divisor of cout_pad (multiple of 16, <= 128) minimising waves * (steps * step clocks + epilogue); a step is
+  // 6 MMAs = 3*bn clocks at the MMA floor, ~300 clocks of issue / barrier latency, or its weight bytes at the L2 rate
   int block_n = 16;
   {
     const int64_t m_tiles = (int64_t)a->x.n * p.tiles_y * p.tiles_x * nprob;
     double best = -1.0;
-    for (int bn = 16; bn <= 256 && bn <= cout_pad; bn += 16) {
+    for (int bn = 16; bn <= T32_MAX_N && bn <= cout_pad; bn += 16) {
       if (cout_pad % bn) continue;
-      if (p.a_stages * p.a_stage_bytes + 2 * bn * 128 > smem_budget) continue;
+      if (a_side + 2 * bn * 64 * T32_PLANES > smem_budget) continue;
       const int64_t tiles = m_tiles * (cout_pad / bn);
       const double waves = (double)((tiles + g_num_sms32 - 1) / g_num_sms32);
-      const double step = fmax(fmax(350.0, 4.0 * bn), (double)(bn * 256) / 56.0);
+      const double step = fmax(fmax(300.0, 3.0 * bn), (double)(bn * 64 * T32_PLANES) / 56.0);
       const double t = waves * ((double)(p.cin_chunks * ntaps) * step + 40.0 * bn + 1500.0);
       if (best < 0 || t < best * 0.999) { best = t; block_n = bn; }
     }
   }
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
-  e.b_half_bytes = block_n * 128;
+  e.b_plane_bytes = block_n * 64;
   {
-    int bst = (smem_budget - p.a_stages * p.a_stage_bytes) / e.b_half_bytes;
+    int bst = (smem_budget - a_side) / (T32_PLANES * e.b_plane_bytes);
     p.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
     VPS_CHECK_ARG(p.b_stages >= 2, "conv2d_tc32: ring does not fit (%d x %d px halo, bn %d)", halo_h, p.halo_w, block_n);
   }
   static int group_env = -1;
-  if (group_env < 0) { const char* ev = getenv("VPS_TC32_GROUP"); group_env = ev ? atoi(ev) : 4; }
+  if (group_env < 0) { const char* ev = getenv("VPS_TC32_GROUP"); group_env = ev ? atoi(ev) : 2; }
   e.group = group_env < 1 ? 1 : group_env;
-  static int neg_env = -1;
-  if (neg_env < 0) { const char* ev = getenv("VPS_TC32_NEG"); neg_env = ev ? atoi(ev) : 0; }
-  e.alt_neg = neg_env;
-  e.nbuf = block_n > 128 ? 2 : 4;
-  e.buf_cols = TMEM_COLS / e.nbuf;
   p.nprob = nprob;
   p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
   p.total_tiles = p.tiles_per_prob * nprob;
@@ -608,7 +629,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   p.stats = nullptr;
   if (p.total_tiles == 0) return VPS_OK;
 
-  CUtensorMap tmA, tmBt, tmBhl;
+  CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->x.c, (cuuint64_t)a->x.w, (cuuint64_t)a->x.h, (cuuint64_t)a->x.n};
     cuuint64_t strides[3] = {(cuuint64_t)a->x.cs * 4, (cuuint64_t)a->x.w * a->x.cs * 4, (cuuint64_t)a->x.h * a->x.w * a->x.cs * 4};
@@ -623,26 +644,16 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   }
   const int64_t n_plane = (int64_t)cout_pad * ntaps * cin_pad;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)ntaps, (cuuint64_t)nprob};
-    cuuint64_t strides[3] = {(cuuint64_t)ntaps * cin_pad * 4, (cuuint64_t)cin_pad * 4, (cuuint64_t)n_plane * 4};
-    cuuint32_t box[4] = {(cuuint32_t)T32_KC, (cuuint32_t)block_n, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmBt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a->w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc32: encode Bt failed (%d)", (int)r); return VPS_E_CUDA; }
-  }
-  {
-    cuuint64_t dims[5] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)ntaps, (cuuint64_t)nprob, 2};
+    cuuint64_t dims[5] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)ntaps, (cuuint64_t)nprob, T32_PLANES};
     cuuint64_t strides[4] = {(cuuint64_t)ntaps * cin_pad * 2, (cuuint64_t)cin_pad * 2, (cuuint64_t)n_plane * 2,
                              (cuuint64_t)n_plane * nprob * 2};
-    cuuint32_t box[5] = {(cuuint32_t)T32_KC, (cuuint32_t)block_n, 1, 1, 2};
+    cuuint32_t box[5] = {(cuuint32_t)T32_KC, (cuuint32_t)block_n, 1, 1, T32_PLANES};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmBhl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (char*)a->w + 4 * n_plane * nprob, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc32: encode Bhl failed (%d)", (int)r); return VPS_E_CUDA; }
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, (void*)a->w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc32: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
-  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * e.b_half_bytes + 1024 + T32_BAR_BYTES;
+  const int smem = a_side + p.b_stages * T32_PLANES * e.b_plane_bytes + 1024 + T32_BAR_BYTES;
   static bool smem_set = false;
   if (!smem_set) {
     if (cudaFuncSetAttribute(conv_igemm_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -661,7 +672,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_tc32_kernel, tmA, tmBt, tmBhl, p, e);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_tc32_kernel, tmA, tmB, p, e);
   if (le != cudaSuccess) { vps::set_error("conv2d_tc32: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
   VPS_CUDA_LAST("conv_igemm_tc32_kernel");
   return VPS_OK;

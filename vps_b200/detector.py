@@ -331,6 +331,9 @@ class PanopticFuseTrack(nn.Module):
         det_rois, cls_idx, cls_prob, kout = st['det_rois'], st['cls_idx'], st['cls_prob'], st['kout']
         ops.SCOPE[0] = 'track_mask_fuse'
         k, dummy = [int(v) for v in kout.tolist()]            # 8-byte read-back: number of detections
+        if self.precision == "tc32" and ops.tc32_overflow():
+            raise ops.VpsError("tc32: an activation or weight exceeded the fp16 range (65504) of the main tensor-core "
+                               "product; use precision='fp32' for this input")
         iid = meta['iid']
         is_first = (iid % 10000) == 1
         det_roi_feats = self.bbox_roi_extractor(xf, det_rois, k)

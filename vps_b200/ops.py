@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, VPS_BF16, VPS_F32, VpsConvArgs,
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, VPS_BF16, VPS_F32, VpsConvArgs, VpsError,
                    VpsTensor, check, lib)
 
 _DT = {torch.float32: VPS_F32, torch.bfloat16: VPS_BF16}
@@ -157,7 +157,7 @@ class PackedConv:
         return self._tc[gran]
 
     def tc32(self):
-        """[tf32 | bf16 | bf16] planes of the fp32-parity tensor-core kernel (vps_conv2d_tc32)."""
+        """[fp16 | bf16 | bf16] planes of the fp32-parity tensor-core kernel (vps_conv2d_tc32)."""
         if self._tc32 is None:
             self._tc32 = pack_tc32([self])
         return self._tc32
@@ -192,6 +192,11 @@ def pack_tc32(pws):
 # fp32 activations: True = tensor cores with split operands (vps_conv2d_tc32, the "tc32" parity precision),
 # False = CUDA-core fp32 FMA (vps_conv2d_simt, the debugging reference of the parity mode)
 F32_TC = [False]
+
+
+def tc32_overflow(reset=True):
+    """threads of the tc32 kernels that met |value| > 65504 (the fp16 range of the main product) since the last reset"""
+    return int(lib().vps_tc32_overflow(int(reset)))
 
 
 def f32_tc_ok(x):
