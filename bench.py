@@ -319,7 +319,10 @@ def run_gpu_arm(args):
         for name, s, e, fl, tag, scope in rec:
             a = agg.setdefault(name, [0.0, 0.0, 0])
             a[0] += s.elapsed_time(e); a[1] += fl; a[2] += 1
-        tc_ms, tc_fl, tc_n = agg.get("vps_conv2d_tc", [0.0, 0.0, 0])
+        tc_ms, tc_fl, tc_n = 0.0, 0.0, 0
+        for kname in ("vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_conv2d_tc32", "vps_conv2d_tc32_multi"):
+            a_ = agg.get(kname, [0.0, 0.0, 0])
+            tc_ms, tc_fl, tc_n = tc_ms + a_[0], tc_fl + a_[1], tc_n + a_[2]
         pk = peaks()
         if tc_ms > 0:
             ach = tc_fl / (tc_ms * 1e-3) / 1e12
@@ -404,7 +407,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="tc32", choices=["tc32", "bf16", "fp32"])
     ap.add_argument("--height", type=int, default=H_FULL)
     ap.add_argument("--width", type=int, default=W_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")

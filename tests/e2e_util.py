@@ -87,3 +87,19 @@ def compare_frame(oracle, prod, img, ref, iid, device="cuda:0"):
     rep["ids_kept_equal"] = bool(np.array_equal(p_res[2]["panoptic_det_obj_ids"].cpu().numpy(),
                                                 o_res[2]["panoptic_det_obj_ids"].numpy()))
     return rep, (o_res, ot), (p_res, pt)
+
+
+def near_tie_report(prod_map, oracle_map, oracle_logits, tol):
+    """Label maps of two correct fp32 implementations may differ where the argmax is decided by less than their logit
+    error.  Returns (pixels that differ, differing pixels NOT explained by an oracle top-2 logit margin <= tol)."""
+    pm, om = prod_map.reshape(-1).long(), oracle_map.reshape(-1).long()
+    bad = (pm != om).nonzero().flatten()
+    if bad.numel() == 0:
+        return 0, 0
+    lg = oracle_logits.reshape(oracle_logits.shape[1], -1)[:, bad]          # [C, nbad]
+    top2 = lg.topk(2, dim=0).values
+    margin = top2[0] - top2[1]
+    # the product's label must be one of the (near-)tied candidates
+    prod_logit = lg.gather(0, pm[bad].clamp(max=lg.shape[0] - 1).view(1, -1))[0]
+    explained = (margin <= tol) & ((top2[0] - prod_logit) <= tol)
+    return int(bad.numel()), int((~explained).sum())

@@ -108,11 +108,12 @@ def test_dummy_detection_path(models):
         prod.prepare(force=True)
 
 
-def test_cuda_graph_replay_equals_eager(models):
+@pytest.mark.parametrize("precision", ["tc32", "fp32"])
+def test_cuda_graph_replay_equals_eager(models, precision):
     """The static part replayed as a CUDA graph gives bit-identical results to eager launches, across frames with
     different inputs (static buffers are refreshed) and with the tracker state carried in the eager tail."""
     _, prod = models
-    prod.precision = "fp32"
+    prod.precision = precision
     H, W = 128, 256
     frames = [make_pair(H, W, seed=s) for s in (1, 2, 3, 4)]
     outs = {}
@@ -137,7 +138,7 @@ def test_clip_runner_equals_direct_calls(models):
     simple_test calls return for the same clip (int64 maps), including the tracker ids carried across frames."""
     from vps_b200.runner import ClipRunner
     _, prod = models
-    prod.precision = "fp32"
+    prod.precision = "tc32"
     H, W = 128, 256
     frames = [make_pair(H, W, seed=s) for s in (5, 6, 7, 8, 9, 10, 11, 12)]
     metas = [meta(10001 + f, H, W) for f in range(len(frames))]
@@ -194,13 +195,15 @@ def test_clip_runner_unified_pan_result(models):
         assert np.array_equal(g, e)
 
 
-def test_viper_aspect_fp32_matches_oracle(models):
+@pytest.mark.parametrize("precision", ["tc32", "fp32"])
+def test_viper_aspect_fp32_matches_oracle(models, precision):
     """BASELINE config 4 shape family (1088x1920 = 17x30 blocks of 64): a small frame of the same odd block counts
     (192x320 = 3x5 blocks) through the fp32 path: detections, class ids, kept set and track ids equal the oracle's, label
     maps agree up to argmax near-ties."""
     oracle, prod = models
-    prod.precision = "fp32"
+    prod.precision = precision
     prod.reset_tracker()
+    oracle.prev_bboxes = None
     H, W = 192, 320
     img, ref = make_pair(H, W, seed=31)
     for iid, (a, b) in ((10001, (img, ref)), (10002, (ref, img))):

@@ -105,7 +105,8 @@ def _product_clip(prod, frames, H, W, precision):
 def test_vpq_parity_of_the_whole_chain(cuda):
     """BASELINE metric 'VPQ parity': a 5-frame clip through the product (model -> unified pan result -> segments, all on
     the GPU) evaluated with the GPU VPQ evaluator against the same chain of the oracle on the CPU as ground truth.
-    fp32 mode: every tube matches with IoU 1 (VPQ = 100 for all window lengths).  bf16 mode: the agreement is reported (with
+    tc32 (tensor-core parity precision) and fp32 (CUDA-core twin): every tube matches with IoU 1 (VPQ = 100 for all window
+    lengths).  bf16 mode: the agreement is reported (with
     random-init weights the logits are noise-like, so small perturbations move whole segments: measured PQ 0.71 at k = 1)
     and only checked to be a valid, non-zero score -- it is the accuracy cost of the fast mode in the units the reference is evaluated in."""
     from tests.e2e_util import build_models, make_pair
@@ -115,7 +116,7 @@ def test_vpq_parity_of_the_whole_chain(cuda):
     H, W = 128, 256
     frames = [make_pair(H, W, seed=s) for s in (51, 52, 53, 54, 55)]
     gt = _oracle_clip(oracle, frames, H, W)
-    for precision in ("fp32", "bf16"):
+    for precision in ("tc32", "fp32", "bf16"):
         pred = _product_clip(prod, frames, H, W, precision)
         ev = P.VpqEvaluator(CATEGORIES)
         for (gi, gs), (pi, ps) in zip(gt, pred):
@@ -124,7 +125,7 @@ def test_vpq_parity_of_the_whole_chain(cuda):
             stat = ev.compute(nframes)
             res, _ = P.pq_average(stat, CATEGORIES, isthing=None)
             print("VPQ agreement %s k=%d: PQ %.4f SQ %.4f RQ %.4f (n=%d)" % (precision, nframes, res["pq"], res["sq"], res["rq"], res["n"]))
-            if precision == "fp32":
+            if precision in ("tc32", "fp32"):
                 assert res["pq"] == 1.0 and res["sq"] == 1.0 and res["rq"] == 1.0, (nframes, res)
             else:      # reported, not gated: with random-init weights whole segments flip on 1e-2 feature perturbations
                 assert 0.0 < res["pq"] <= 1.0 and res["n"] > 0, (nframes, res)

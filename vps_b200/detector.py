@@ -48,7 +48,7 @@ class PanopticFuseTrack(nn.Module):
 
     def __init__(self, backbone, rpn_head, bbox_roi_extractor, bbox_head, mask_roi_extractor, mask_head, train_cfg,
                  test_cfg, neck=None, extra_neck=None, panoptic=None, track_head=None, shared_head=None,
-                 pretrained=None, precision="bf16"):
+                 pretrained=None, precision="tc32"):
         super().__init__()
         assert shared_head is None
         self.backbone = build_backbone(backbone)
