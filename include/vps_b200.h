@@ -116,6 +116,11 @@ int vps_pack_weights_tc32(const float* w_oihw, const float* scale, void* dst, in
                           int transposed, int prob, int nprob, void* stream);
 int64_t vps_packed_tc32_bytes(int cout, int cin, int kh, int kw, int nprob);
 int vps_tc32_overflow(int reset);
+/* fused DCNv1 3x3 in the tc32 precision (deform_conv.py:15-87 forward; deform_conv_cuda.cpp:152-260 = deformable_im2col +
+ * GEMM): the sampling warps write the split operand planes straight into the tensor-core ring, no column matrix.
+ * x fp32 NHWC (c % 32 == 0), offset fp32 NHWC [..,18], w = vps_pack_weights_tc32 buffer of the [cout,cin,3,3] kernel. */
+int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offset, const void* w, int cout, const vps_tensor* y,
+                         void* stream);
 
 /* explicit im2col for small-cin layers feeding vps_conv2d_tc as a 1x1 conv: cols is NHWC
  * [n, oh, ow, kpad] with k = (r*kw+s)*cin + ci, zero padded to cols.c. */

@@ -175,6 +175,33 @@ def test_deform_conv_tc_fused(cuda):
         assert float((got - ref).abs().max()) <= 2e-2 * max(1.0, float(ref.abs().max()))
 
 
+def test_deform_conv_tc32_fused(cuda):
+    """vps_deform_conv_tc32 (fp32 activations, sampling warps feed the split fp16 operand planes) vs the oracle DCNv1
+    (deform_conv_cuda forward) in fp32: ragged tiles, offsets that leave the image, two images, cout > 128 (two N tiles)."""
+    from oracle import ops as O
+    from vps_b200 import ops
+    g = torch.Generator().manual_seed(16)
+    old = ops.F32_TC[0]
+    ops.F32_TC[0] = True
+    try:
+        for (N, C, Co, H, W) in [(1, 128, 128, 19, 37), (2, 256, 256, 12, 20), (1, 64, 32, 8, 16), (1, 256, 128, 64, 128)]:
+            x = torch.randn(N, C, H, W, generator=g)
+            off = torch.randn(N, 18, H, W, generator=g) * 3.0
+            off[:, :, 0, :] -= 4.0                       # some samples fall outside the image
+            w = torch.randn(Co, C, 3, 3, generator=g) / (C * 9) ** 0.5
+            ref = O.deform_conv(x, off, w)
+            pk = ops.PackedConv(w.cuda(), None)
+            y = torch.full((N, H, W, Co), float("nan"), dtype=torch.float32, device="cuda")
+            ops.deform_conv_tc32(to_nhwc(x), to_nhwc(off), pk, y)
+            torch.cuda.synchronize()
+            got = y.permute(0, 3, 1, 2).cpu()
+            assert not torch.isnan(got).any()
+            assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max())), (N, C, Co, H, W)
+        assert ops.tc32_overflow() == 0
+    finally:
+        ops.F32_TC[0] = old
+
+
 def test_roi_align_multilevel(cuda):
     from oracle.model import roi_extract
     from vps_b200 import ops

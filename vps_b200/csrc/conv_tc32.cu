@@ -58,7 +58,15 @@ struct Tc32Extra {
   int b_plane_bytes;         // block_n * 64: one weight plane of one step
   int nk_last;               // K16 slabs of the last channel chunk that hold real channels
   int group;                 // K steps of the main product accumulated inside the tensor core before promotion
+  int dcn;                   // 1: the operand planes are produced by the deformable-sampling warps (no activation TMA)
 };
+
+struct Dcn32Params {
+  const float* x;
+  const float* off;
+  int x_cs, off_cs, H, W;
+};
+constexpr int DCN32_SETUP_BYTES = 9 * BLOCK_M * 32;      // per (tap, pixel): 4 bilinear weights + 4 element offsets
 
 struct Ring32 {
   uint32_t s_base, s_bytes;      // staging ring
@@ -140,7 +148,7 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
     for (int cc = 0; cc < p.cin_chunks; ++cc) {
       int r = 0, s = 0;
       for (int tap = 0; tap < ntaps; ++tap) {
-        if (!halo || tap == 0) {
+        if (!e.dcn && (!halo || tap == 0)) {
           mbar_wait(rg.sempty(ss), sphase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(rg.sfull(ss), a_box_bytes);
@@ -210,6 +218,99 @@ __device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Ext
     }
   }
   if (over) atomicAdd(&g_tc32_overflow, 1u);
+}
+
+
+// ---------------------------------------------------------------- DCNv1: warps 2..7 sample the operand planes (fused im2col)
+// deformable_im2col (deform_conv_cuda_kernel.cu:189-242) for a 3x3 / stride 1 / pad 1 / dilation 1 kernel with one deformable
+// group: column (tap k, channel c) of output pixel (y, x) = bilinear sample of x[c] at (y - 1 + k/3 + dy_k, x - 1 + k%3 + dx_k),
+// zero outside (-1, H) x (-1, W), corner taps outside the image contribute 0.  The sampled fp32 value is split into the two
+// fp16 planes straight into the operand ring -- the 9x column matrix (1.2 GB per P2 layer in fp32) never exists.  K steps run
+// chunk-major / tap-minor: the nine taps of a 32-channel chunk re-read the same few KB of input from L1.
+__device__ __forceinline__ void dcn_gather32(const ConvTcParams& p, const Tc32Extra& e, const Dcn32Params& d, const Ring32& rg,
+                                             uint32_t setup_base, int gtid) {
+  constexpr int NT = 32 * T32_CONV_WARPS;
+  const int H = d.H, W = d.W;
+  int as = 0;
+  uint32_t aphase = 0;
+  const int j = gtid & 3;                    // 8-channel group of the 32-channel chunk
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const TileCoord t = tile_coord(p, tile);
+    // ---- sampling set-up of all (tap, pixel) pairs of this tile
+    for (int item = gtid; item < 9 * BLOCK_M; item += NT) {
+      const int k = item >> 7, r = item & (BLOCK_M - 1);
+      const int ty_in = r / p.tw, tx_in = r - ty_in * p.tw;
+      const int yo = t.ty * p.th + ty_in, xo = t.tx * p.tw + tx_in;
+      float wts[4] = {0.f, 0.f, 0.f, 0.f};
+      int offs[4] = {0, 0, 0, 0};
+      if (yo < H && xo < W) {
+        const float* op = d.off + ((int64_t)(t.img * H + yo) * W + xo) * d.off_cs;
+        const float oh = __ldg(op + 2 * k), ow = __ldg(op + 2 * k + 1);
+        const float h = (float)(yo - 1 + k / 3) + oh;
+        const float w = (float)(xo - 1 + k % 3) + ow;
+        if (h > -1.f && w > -1.f && h < (float)H && w < (float)W) {
+          const int hl = (int)floorf(h), wl = (int)floorf(w);
+          const int hh_ = hl + 1, wh_ = wl + 1;
+          const float lh = h - (float)hl, lw = w - (float)wl;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const int base = t.img * H;
+          if (hl >= 0 && wl >= 0) { wts[0] = hh * hw; offs[0] = ((base + hl) * W + wl) * d.x_cs; }
+          if (hl >= 0 && wh_ <= W - 1) { wts[1] = hh * lw; offs[1] = ((base + hl) * W + wh_) * d.x_cs; }
+          if (hh_ <= H - 1 && wl >= 0) { wts[2] = lh * hw; offs[2] = ((base + hh_) * W + wl) * d.x_cs; }
+          if (hh_ <= H - 1 && wh_ <= W - 1) { wts[3] = lh * lw; offs[3] = ((base + hh_) * W + wh_) * d.x_cs; }
+        }
+      }
+      const uint32_t sa = setup_base + (uint32_t)item * 32u;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(wts[0]), "f"(wts[1]), "f"(wts[2]), "f"(wts[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16u), "r"(offs[0]), "r"(offs[1]), "r"(offs[2]), "r"(offs[3]) : "memory");
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+      const float* xc = d.x + cc * T32_KC + j * 8;
+      for (int k = 0; k < 9; ++k) {
+        mbar_wait(rg.pempty(as), aphase ^ 1);
+        const uint32_t dst = rg.a_base + as * rg.a_bytes;
+        for (int r = gtid >> 2; r < BLOCK_M; r += NT / 4) {
+          const uint32_t sa = setup_base + (uint32_t)(k * BLOCK_M + r) * 32u;
+          float wq[4];
+          int oq[4];
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wq[0]), "=f"(wq[1]), "=f"(wq[2]), "=f"(wq[3]) : "r"(sa));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(oq[0]), "=r"(oq[1]), "=r"(oq[2]), "=r"(oq[3]) : "r"(sa + 16u));
+          float acc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+          // the reference accumulates w1*v1 + w2*v2 + w3*v3 + w4*v4 left to right (dmcn_im2col_bilinear); same order here
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {           // corners outside the image carry weight 0 (branch-free: finite inputs)
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(xc + oq[c]));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(xc + oq[c]) + 1);
+            acc[0] += wq[c] * v0.x; acc[1] += wq[c] * v0.y; acc[2] += wq[c] * v0.z; acc[3] += wq[c] * v0.w;
+            acc[4] += wq[c] * v1.x; acc[5] += wq[c] * v1.y; acc[6] += wq[c] * v1.z; acc[7] += wq[c] * v1.w;
+          }
+          unsigned short hb[8], lb[8];
+          bool over = false, dummy = false;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float lo = acc[q] - to_f16_sat(acc[q], hb[q], over);
+            to_f16_sat(lo * T32_LO_SCALE, lb[q], dummy);
+          }
+          if (over) atomicAdd(&g_tc32_overflow, 1u);
+          const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
+          const uint32_t pm = dst + off, pl = pm + (uint32_t)e.plane_bytes;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"((uint32_t)hb[0] | ((uint32_t)hb[1] << 16)),
+                       "r"((uint32_t)hb[2] | ((uint32_t)hb[3] << 16)), "r"((uint32_t)hb[4] | ((uint32_t)hb[5] << 16)),
+                       "r"((uint32_t)hb[6] | ((uint32_t)hb[7] << 16)) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"((uint32_t)lb[0] | ((uint32_t)lb[1] << 16)),
+                       "r"((uint32_t)lb[2] | ((uint32_t)lb[3] << 16)), "r"((uint32_t)lb[4] | ((uint32_t)lb[5] << 16)),
+                       "r"((uint32_t)lb[6] | ((uint32_t)lb[7] << 16)) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(rg.pfull(as));
+        if (++as == p.a_stages) { as = 0; aphase ^= 1; }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");      // the set-up table is rewritten for the next tile
+  }
 }
 
 // ---------------------------------------------------------------- warp 1: MMA issuer
@@ -432,6 +533,58 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   }
 
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- fused DCNv1 kernel (same pipeline, sampling warps feed the ring)
+constexpr int DCN32_REGS_LOW = 88, DCN32_REGS_HIGH = 168;      // 256 * 88 + 256 * 168 = 65536
+__global__ void __launch_bounds__(T32_THREADS, 1)
+dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const Tc32Extra e, const Dcn32Params d) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  Ring32 rg;
+  rg.s_base = smem_base; rg.s_bytes = 0;
+  rg.a_base = smem_base; rg.a_bytes = (uint32_t)T32_PLANES * (uint32_t)e.plane_bytes;
+  rg.b_base = rg.a_base + (uint32_t)p.a_stages * rg.a_bytes; rg.b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
+  const uint32_t setup_base = rg.b_base + (uint32_t)p.b_stages * rg.b_bytes;
+  rg.bar_base = setup_base + DCN32_SETUP_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 2) {
+    for (int i = lane; i < T32_NBAR; i += 32) {
+      uint32_t count = 1;
+      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;
+      if ((i >= 6 * MAX_STAGES + 2 && i < 6 * MAX_STAGES + 4) || i >= 6 * MAX_STAGES + 6) count = 32 * T32_EPI_WARPS;
+      mbar_init(rg.bar_base + 8u * i, count);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rg.tmem_slot()), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(rg.tmem_slot()) : "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCN32_REGS_LOW));
+    if (warp == 0) producer32(p, e, rg, &tmB, &tmB);
+    else if (warp == 1) mma32(p, e, rg, tmem_base);
+    else dcn_gather32(p, e, d, rg, setup_base, (int)threadIdx.x - 64);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCN32_REGS_HIGH));
+    promote_epilogue<VPS_ACT_NONE>(p, e, rg, tmem_base, warp, lane);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -679,3 +832,102 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
 }
 
 extern "C" int vps_conv2d_tc32(const vps_conv_args* a, void* stream) { return vps_conv2d_tc32_multi(a, 1, stream); }
+
+
+// Fused DCNv1 3x3 / stride 1 / pad 1 / dilation 1 / 1 deformable group in the tc32 precision (deform_conv.py:15-87 forward,
+// deform_conv_cuda.cpp:152-260): x fp32 NHWC (c % 32 == 0), offset fp32 NHWC [.., 18] = (dy, dx) per tap,
+// w = vps_pack_weights_tc32 buffer of the [cout, cin, 3, 3] kernel, y fp32 NHWC.  No bias (DeformConv has none).
+extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offset, const void* w, int cout, const vps_tensor* y,
+                                    void* stream) {
+  VPS_CHECK_ARG(x->dtype == VPS_F32 && offset->dtype == VPS_F32 && offset->c >= 18, "deform_conv_tc32: dtypes");
+  VPS_CHECK_ARG(x->c % T32_KC == 0 && x->cs % 4 == 0 && ((uintptr_t)x->ptr & 15) == 0, "deform_conv_tc32: x must have cin %% 32 == 0");
+  VPS_CHECK_ARG(offset->n == x->n && offset->h == x->h && offset->w == x->w && y->n == x->n && y->h == x->h && y->w == x->w &&
+                    y->c == cout, "deform_conv_tc32: shapes");
+  VPS_CHECK_ARG((int64_t)x->n * x->h * x->w * x->cs < (1ll << 31), "deform_conv_tc32: tensor too large for 32-bit offsets");
+  VPS_CHECK_ARG(((uintptr_t)w & 127) == 0, "deform_conv_tc32: weights not aligned");
+  auto encode = get_encode32();
+  if (!encode) { vps::set_error("cuTensorMapEncodeTiled unavailable"); return VPS_E_CUDA; }
+  if (!g_num_sms32) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms32, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms32 <= 0) { vps::set_error("no device"); return VPS_E_NODEV; }
+  }
+  const int cout_pad = (cout + 15) / 16 * 16;
+  ConvTcParams p = {};
+  Tc32Extra e = {};
+  p.bk = T32_KC; p.nprob = 1;
+  p.n_img = x->n; p.oh = x->h; p.ow = x->w;
+  int best_tw = 16; int64_t best_area = -1;
+  const int cands[5] = {16, 8, 32, 64, 128};
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cands[i], th = 128 / tw;
+    const int64_t area = (int64_t)vps::cdiv(x->w, tw) * tw * vps::cdiv(x->h, th) * th;
+    if (best_area < 0 || area < best_area) { best_area = area; best_tw = tw; }
+  }
+  p.tw = best_tw; p.th = 128 / best_tw;
+  p.tiles_x = vps::cdiv(x->w, p.tw); p.tiles_y = vps::cdiv(x->h, p.th);
+  int block_n = cout_pad;
+  while (block_n > T32_MAX_N || cout_pad % block_n) block_n -= 16;
+  p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
+  p.kh = p.kw = 3; p.sh = p.sw = 1; p.halo = 0; p.halo_w = 0;
+  p.cin_chunks = x->c / T32_KC;
+  e.rows = BLOCK_M; e.dcn = 1;
+  e.plane_bytes = BLOCK_M * 64; e.stage_bytes = 0; e.nk_last = 2;
+  e.b_plane_bytes = block_n * 64;
+  p.a_box_bytes = 0; p.a_stage_bytes = T32_PLANES * e.plane_bytes;
+  p.a_stages = 3;
+  {
+    const int budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64 - DCN32_SETUP_BYTES - p.a_stages * p.a_stage_bytes;
+    int bst = budget / (T32_PLANES * e.b_plane_bytes);
+    p.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
+    VPS_CHECK_ARG(p.b_stages >= 2, "deform_conv_tc32: ring does not fit");
+  }
+  static int group_env = -1;
+  if (group_env < 0) { const char* ev = getenv("VPS_TC32_GROUP"); group_env = ev ? atoi(ev) : 1; }
+  e.group = group_env < 1 ? 1 : group_env;
+  p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  p.total_tiles = p.tiles_per_prob;
+  p.y = y->ptr; p.y_h = y->h; p.y_w = y->w; p.y_cs = y->cs; p.y_dtype = y->dtype;
+  const int esz = y->dtype == VPS_BF16 ? 2 : 4;
+  p.y_vec = (((uintptr_t)y->ptr & 15) == 0) && ((y->cs * esz) % 16 == 0);
+  if (p.y_vec && (((uintptr_t)y->ptr & 31) == 0) && ((y->cs * esz) % 32 == 0)) p.y_vec = 2;
+  p.oy_mul = p.ox_mul = 1;
+  p.res = nullptr; p.bias = nullptr; p.cout = cout; p.act = VPS_ACT_NONE; p.slope = 0.f; p.out_scale = 1.f;
+  p.stats = nullptr;
+  if (p.total_tiles == 0) return VPS_OK;
+  Dcn32Params d;
+  d.x = (const float*)x->ptr; d.off = (const float*)offset->ptr; d.x_cs = x->cs; d.off_cs = offset->cs; d.H = x->h; d.W = x->w;
+  CUtensorMap tmB;
+  {
+    const int64_t n_plane = (int64_t)cout_pad * 9 * x->c;
+    cuuint64_t dims[5] = {(cuuint64_t)x->c, (cuuint64_t)cout_pad, 9, 1, T32_PLANES};
+    cuuint64_t strides[4] = {(cuuint64_t)9 * x->c * 2, (cuuint64_t)x->c * 2, (cuuint64_t)n_plane * 2, (cuuint64_t)n_plane * 2};
+    cuuint32_t box[5] = {(cuuint32_t)T32_KC, (cuuint32_t)block_n, 1, 1, T32_PLANES};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vps::set_error("deform_conv_tc32: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
+  }
+  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * T32_PLANES * e.b_plane_bytes + DCN32_SETUP_BYTES + 1024 + T32_BAR_BYTES;
+  static bool smem_set = false;
+  if (!smem_set) {
+    if (cudaFuncSetAttribute(dcn_igemm_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      vps::set_error("deform_conv_tc32: cannot raise dynamic smem: %s", cudaGetErrorString(cudaGetLastError()));
+      return VPS_E_CUDA;
+    }
+    smem_set = true;
+  }
+  const int grid = p.total_tiles < g_num_sms32 ? p.total_tiles : g_num_sms32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T32_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, dcn_igemm_tc32_kernel, tmB, p, e, d);
+  if (le != cudaSuccess) { vps::set_error("deform_conv_tc32: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
+  VPS_CUDA_LAST("dcn_igemm_tc32_kernel");
+  return VPS_OK;
+}

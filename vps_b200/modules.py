@@ -370,6 +370,10 @@ class UPSNetFPN(_Prepared):
                 # fused: sampled columns go straight into the tensor-core operand ring (no 9x column matrix in HBM)
                 y = empty_nhwc(n, h, w, L['pk3'].cout, x.dtype, x.device)
                 ops.deform_conv_tc(x, off, L['pk3'], y)
+            elif ops.f32_tc_ok(x) and x.shape[3] % 32 == 0:
+                # tc32 parity precision: same fusion with fp32 activations split into fp16 operand planes by the sampling warps
+                y = empty_nhwc(n, h, w, L['pk3'].cout, x.dtype, x.device)
+                ops.deform_conv_tc32(x, off, L['pk3'], y)
             else:
                 cols = empty_nhwc(n, h, w, 9 * x.shape[3], x.dtype, x.device)
                 ops.deform_im2col(x, off, cols)

@@ -405,6 +405,16 @@ def deform_conv_tc(x, offset, pw, y):
     return y
 
 
+def deform_conv_tc32(x, offset, pw, y):
+    """fused DCNv1 3x3 in the tc32 precision: x fp32 NHWC, offset f32 NHWC [..,18], pw = PackedConv of the OIHW kernel"""
+    if PROFILE is not None:
+        _NOTE["flops"] = 2 * x.shape[0] * x.shape[1] * x.shape[2] * pw.cout * pw.cin * 9
+        _NOTE["tag"] = "dcn3x3 %d->%d @%dx%d" % (pw.cin, pw.cout, x.shape[1], x.shape[2])
+    check(lib().vps_deform_conv_tc32(_bt(x), _bt(offset), C.c_void_p(pw.tc32().data_ptr()), pw.cout, _bt(y), stream()),
+          "deform_conv_tc32")
+    return y
+
+
 # ------------------------------------------------------------------ detection
 def roi_align(feats, strides, rois, nroi, out, sample_num=2, nroi_dev=None):
     arr = (VpsTensor * len(feats))(*[vt(f) for f in feats])
