@@ -27,10 +27,10 @@
 // Pipeline per CTA (persistent, one 128-pixel x block_n (<= 128) tile at a time, K consumed 32 channels per step):
 //   warp 0     : TMA producer: raw fp32 activation boxes {32 ch, pixels} into a staging ring; pre-split weight tiles
 //                [B | B2] (vps_pack_weights_tc32) into the B ring.
-//   warps 2-7  : converters: staging box -> two SWIZZLE_64B operand planes A, A2
+//   warps 3-7  : converters: staging box -> two SWIZZLE_64B operand planes A, A2
 //                (generic-proxy writes -> fence.proxy.async -> mbarrier).  In halo mode (stride 1, > 1 tap) one converted
 //                (th+kh-1) x (tw+kw-1) box feeds all kh*kw taps through shifted descriptor start addresses.
-//   warp 1     : MMA issuer: 6 x tcgen05.mma.kind::f16 (M128 x N x K16) per (tap, 32-channel chunk).
+//   warps 1, 2 : MMA issuers (main product / corrections): 2 + 4 tcgen05.mma.kind::f16 (M128 x N x K16) per (tap, 32-channel chunk).
 //   warps 8-15 : promotion + epilogue: tcgen05.ld finished groups, RN-add into registers (setmaxnreg gives these two
 //                warpgroups 200 registers), finally bias / activation / residual and the NHWC store (conv_tc.cu's epilogue).
 #include <cuda_fp16.h>
@@ -40,11 +40,13 @@
 namespace {
 
 constexpr int T32_EPI_WARPS = 8;            // warps 8..15: two per TMEM lane quarter, alternating 32-column chunks
-constexpr int T32_CONV_WARPS = 6;           // warps 2..7
-constexpr int T32_THREADS = 64 + 32 * (T32_EPI_WARPS + T32_CONV_WARPS);     // 512 = 4 warpgroups
-constexpr int T32_REGS_LOW = 56, T32_REGS_HIGH = 200;    // setmaxnreg: 256 * 56 + 256 * 200 = 65536
+constexpr int T32_CONV_WARPS = 5;           // warps 3..7 (warp 0 = TMA, warp 1 = main-product issuer, warp 2 = correction issuer)
+constexpr int T32_THREADS = 96 + 32 * (T32_EPI_WARPS + T32_CONV_WARPS);     // 512 = 4 warpgroups
+constexpr int T32_REGS_LOW = 64, T32_REGS_HIGH = 192;    // setmaxnreg: 256 * 64 + 256 * 192 = 65536
 constexpr int T32_KC = 32;                  // channels per K step: 64-byte operand rows (SWIZZLE_64B), 2 x K16
-constexpr int T32_MAX_N = 128;              // TMEM: 2 main (ping-pong groups) + 2 correction (per tile) buffers of 128 columns
+constexpr int T32_MAX_N = 128;              // TMEM: block_n <= 64: 6 main (group) + 2 correction (tile) buffers of 64 columns,
+                                            //       block_n <= 128: 3 main + 1 correction buffer of 128 columns
+constexpr int T32_MAX_MAIN = 8;
 constexpr int T32_STAGE_SLOTS = 2;          // fp32 staging boxes (TMA -> converters)
 constexpr int T32_PLANES = 2;               // operand planes: fp16(v), fp16(2^11 (v - fp16(v)))
 constexpr float T32_LO_SCALE = 2048.f, T32_LO_INV = 1.f / 2048.f;
@@ -59,6 +61,7 @@ struct Tc32Extra {
   int nk_last;               // K16 slabs of the last channel chunk that hold real channels
   int group;                 // K steps of the main product accumulated inside the tensor core before promotion
   int dcn;                   // 1: the operand planes are produced by the deformable-sampling warps (no activation TMA)
+  int nmain, ncorr, buf_cols;   // TMEM accumulator buffers: nmain group buffers, then ncorr correction buffers, buf_cols apart
 };
 
 struct Dcn32Params {
@@ -80,13 +83,14 @@ struct Ring32 {
   __device__ __forceinline__ uint32_t bfull(int s) const { return bar_base + 8u * (4 * MAX_STAGES + s); }
   __device__ __forceinline__ uint32_t bempty(int s) const { return bar_base + 8u * (5 * MAX_STAGES + s); }
   __device__ __forceinline__ uint32_t gfull(int a) const { return bar_base + 8u * (6 * MAX_STAGES + a); }
-  __device__ __forceinline__ uint32_t gempty(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 2 + a); }
-  __device__ __forceinline__ uint32_t cfull(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 4 + a); }
-  __device__ __forceinline__ uint32_t cempty(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 6 + a); }
-  __device__ __forceinline__ uint32_t tmem_slot() const { return bar_base + 8u * (6 * MAX_STAGES + 8); }
+  __device__ __forceinline__ uint32_t gempty(int a) const { return bar_base + 8u * (6 * MAX_STAGES + T32_MAX_MAIN + a); }
+  __device__ __forceinline__ uint32_t cfull(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 2 * T32_MAX_MAIN + a); }
+  __device__ __forceinline__ uint32_t cempty(int a) const { return bar_base + 8u * (6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2 + a); }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return bar_base + 8u * (6 * MAX_STAGES + 2 * T32_MAX_MAIN + 4); }
+  __device__ __forceinline__ uint32_t issue_sync() const { return tmem_slot() + 8u; }     // steps issued by the main-product warp
 };
-constexpr int T32_NBAR = 6 * MAX_STAGES + 8;
-constexpr int T32_BAR_BYTES = 8 * (T32_NBAR + 2);
+constexpr int T32_NBAR = 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 4;
+constexpr int T32_BAR_BYTES = 8 * (T32_NBAR + 4);
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3,
                                             int c4) {
@@ -103,6 +107,15 @@ __device__ __forceinline__ uint64_t desc_hi64(uint32_t sbo) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;
   return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 // fp16 (round to nearest, saturating) of v; `over` collects |v| > 65504 (and NaN)
 __device__ __forceinline__ float to_f16_sat(float v, unsigned short& bits, bool& over) {
@@ -313,83 +326,143 @@ __device__ __forceinline__ void dcn_gather32(const ConvTcParams& p, const Tc32Ex
   }
 }
 
-// ---------------------------------------------------------------- warp 1: MMA issuer
+// ---------------------------------------------------------------- warps 1 and 2: MMA issuers
+// One thread can retire a dependent instruction only every ~5 clocks, so the instruction count of the issue loop IS the
+// pipeline rate (measured with VPS_CONV_STATS: a single issuer needed ~1000 clocks per K step for 6 MMAs + 4 barrier
+// operations, against 384 clocks of tensor-pipe time at N = 128).  The work is therefore split by accumulator: warp 1 issues
+// the main product (2 MMAs per step, group buffers), warp 2 the two correction products (4 MMAs per step, the tile's
+// correction buffer); both wait for the same operand / weight barriers and both commit to the slots' empty barriers
+// (arrival count 2).  Descriptors are built from 32-bit halves inside the asm block (no 64-bit integer code in the loop).
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// high word of a K-major SWIZZLE_64B descriptor (64-byte rows): stride byte offset, version 1, layout type 4
+__device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo) { return (sbo >> 4) | (1u << 14) | (4u << 29); }
+
+// ROLE 0: main product (stats slots [0] group-buffer wait, [1] planes, [2] weights, [4] total); ROLE 1: corrections
+// (stats [3] correction-buffer wait)
+template <int ROLE, bool HALO, bool STATS>
 __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base) {
-  const uint32_t nfield = ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-  const uint32_t idesc = (1u << 4) | nfield;                              // D = f32, A = B = f16, K-major
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);   // D = f32, A = B = f16
   const int ntaps = p.kh * p.kw, kw = p.kw;
-  const bool halo = p.halo != 0;
-  const uint32_t hw = (uint32_t)p.halo_w;
-  const uint64_t a_hi = desc_hi64(halo ? hw * 64u : 512u), b_hi = desc_hi64(512u);
-  const uint32_t a_plane = (uint32_t)e.plane_bytes, b_plane = (uint32_t)e.b_plane_bytes;
-  int as = 0, bs = 0, gb = 0, cb = 0;
-  uint32_t aphase = 0, bphase = 0, gphase = 0, cphase = 0;       // gphase / cphase: one parity bit per TMEM buffer
-  const int G = e.group, total_steps = p.cin_chunks * ntaps;
+  const uint32_t row_skip = HALO ? (uint32_t)(p.halo_w - kw) * 4u : 0u;          // descriptor units (16 B) to the next halo row
+  const uint32_t a_hi = desc_hi32(HALO ? (uint32_t)p.halo_w * 64u : 512u), b_hi = desc_hi32(512u);
+  const uint32_t a_plane16 = (uint32_t)e.plane_bytes >> 4, b_plane16 = (uint32_t)e.b_plane_bytes >> 4;
+  const uint32_t a_bytes16 = rg.a_bytes >> 4, b_bytes16 = rg.b_bytes >> 4;
+  const uint32_t a_base16 = (rg.a_base & 0x3FFFF) >> 4, b_base16 = (rg.b_base & 0x3FFFF) >> 4;
+  const int G = e.group, last_cc = p.cin_chunks - 1, a_stages = p.a_stages, b_stages = p.b_stages;
+  const int nbuf = ROLE == 0 ? e.nmain : e.ncorr;
+  const uint32_t buf0 = tmem_base + (ROLE == 0 ? 0u : (uint32_t)(e.nmain * e.buf_cols)), buf_cols = (uint32_t)e.buf_cols;
+  int as = 0, bs = 0, tb = 0;
+  uint32_t aphase = 0, bphase = 0, tphase = 0;       // tphase: one parity bit per TMEM buffer of this role
+  uint32_t nstep = 0;                                // K steps issued so far (all tiles)
+  const uint32_t sync_addr = rg.issue_sync();
+  long long w_t = 0, w_a = 0, w_b = 0;
+  const long long t_begin = STATS ? clock64() : 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    int step = 0, in_group = 0;
-    uint32_t d_main = 0, first = 0, cfirst = 0;
-    // the correction buffer of this tile must have been drained by the promotion warps
-    mbar_wait(rg.cempty(cb), ((cphase >> cb) & 1u) ^ 1u);
-    const uint32_t d_corr = tmem_base + (uint32_t)(2 * T32_MAX_N + cb * T32_MAX_N);
-    for (int cc = 0; cc < p.cin_chunks; ++cc) {
-      const int nk16 = cc == p.cin_chunks - 1 ? e.nk_last : 2;
-      int r = 0, s = 0, a_cur = 0;
-      uint32_t a_slot = 0;
+    int in_group = 0;
+    uint32_t d_tmem = 0, first = 0;
+    for (int cc = 0; cc <= last_cc; ++cc) {
+      const bool two = cc != last_cc || e.nk_last > 1;
+      uint32_t a16 = 0;
+      int sx = 0;
       for (int tap = 0; tap < ntaps; ++tap) {
-        if (in_group == 0) {           // a new group of the main product starts on a drained buffer with accumulate = 0
-          mbar_wait(rg.gempty(gb), ((gphase >> gb) & 1u) ^ 1u);
-          d_main = tmem_base + (uint32_t)(gb * T32_MAX_N);
+        const bool last_step = cc == last_cc && tap == ntaps - 1;
+        if (ROLE == 0 ? in_group == 0 : (cc == 0 && tap == 0)) {
+          // ROLE 0: a new group of the main product starts on a drained buffer with accumulate = 0
+          // ROLE 1: the tile's correction buffer must have been drained by the promotion warps
+          const long long t0 = STATS ? clock64() : 0;
+          mbar_wait(ROLE == 0 ? rg.gempty(tb) : rg.cempty(tb), ((tphase >> tb) & 1u) ^ 1u);
+          if (STATS) w_t += clock64() - t0;
+          d_tmem = buf0 + (uint32_t)tb * buf_cols;
           first = 0;
         }
-        if (!halo || tap == 0) {
+        if (!HALO || tap == 0) {
+          const long long t0 = STATS ? clock64() : 0;
           mbar_wait(rg.pfull(as), aphase);
-          a_cur = as;
-          a_slot = rg.a_base + as * rg.a_bytes;
-          if (++as == p.a_stages) { as = 0; aphase ^= 1; }
+          if (STATS) w_a += clock64() - t0;
+          a16 = a_base16 + (uint32_t)as * a_bytes16;
         }
-        mbar_wait(rg.bfull(bs), bphase);
-        tc_fence_after();
-        ++step;
-        const bool close = (++in_group == G) || step == total_steps;
         {
-          const uint32_t shift = halo ? (uint32_t)(r * (int)hw + s) * 64u : 0u;
-          const uint32_t a_m = a_slot + shift, b_m = rg.b_base + bs * rg.b_bytes;
-          if (elect_one()) {
-            const uint64_t am = a_hi | (uint64_t)((a_m & 0x3FFFF) >> 4), al = a_hi | (uint64_t)(((a_m + a_plane) & 0x3FFFF) >> 4);
-            const uint64_t bm = b_hi | (uint64_t)((b_m & 0x3FFFF) >> 4), bl = b_hi | (uint64_t)(((b_m + b_plane) & 0x3FFFF) >> 4);
-            // main: A x B -> group buffer
-            umma_bf16(d_main, am, bm, idesc, first);
-            if (nk16 > 1) umma_bf16(d_main, am + 2, bm + 2, idesc, 1u);
-            // corrections: A2 x B + A x B2 -> the tile's correction buffer (scaled by 2^-11 when it is added)
-            umma_bf16(d_corr, al, bm, idesc, cfirst);
-            if (nk16 > 1) umma_bf16(d_corr, al + 2, bm + 2, idesc, 1u);
-            umma_bf16(d_corr, am, bl, idesc, 1u);
-            if (nk16 > 1) umma_bf16(d_corr, am + 2, bl + 2, idesc, 1u);
-            umma_commit(rg.bempty(bs));
-            if (!halo || tap == ntaps - 1) umma_commit(rg.pempty(a_cur));
-            if (close) umma_commit(rg.gfull(gb));
-            if (step == total_steps) umma_commit(rg.cfull(cb));
-          }
+          const long long t0 = STATS ? clock64() : 0;
+          mbar_wait(rg.bfull(bs), bphase);
+          if (STATS) w_b += clock64() - t0;
         }
-        first = 1; cfirst = 1;
+        ++nstep;
+        if (ROLE == 1) {
+          // the tensor pipe executes MMAs in issue order: a correction issuer that ran ahead (it never waits for a group
+          // buffer) would queue several steps of its 4-MMA batches in front of the main product and stretch the latency of
+          // every promoted group -- it issues step s only after the main-product warp has issued step s
+          uint32_t seen;
+          do {
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(sync_addr) : "memory");
+          } while ((int32_t)(seen - nstep) < 0);
+        }
+        tc_fence_after();
+        const bool item_done = !HALO || tap == ntaps - 1;
+        const bool close = ROLE == 0 ? (++in_group == G || last_step) : last_step;
+        const uint32_t b16 = b_base16 + (uint32_t)bs * b_bytes16;
+        if (elect_one()) {
+          if (ROLE == 0) {                 // main: A x B
+            umma_f16_lohi(d_tmem, a16, a_hi, b16, b_hi, idesc, first);
+            if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + 2, b_hi, idesc, 1u);
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sync_addr), "r"(nstep) : "memory");
+          } else {                         // corrections: A2 x B + A x B2 (scaled by 2^-11 when the buffer is added)
+            umma_f16_lohi(d_tmem, a16 + a_plane16, a_hi, b16, b_hi, idesc, first);
+            if (two) umma_f16_lohi(d_tmem, a16 + a_plane16 + 2, a_hi, b16 + 2, b_hi, idesc, 1u);
+            umma_f16_lohi(d_tmem, a16, a_hi, b16 + b_plane16, b_hi, idesc, 1u);
+            if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + b_plane16 + 2, b_hi, idesc, 1u);
+          }
+          umma_commit(rg.bempty(bs));
+          if (item_done) umma_commit(rg.pempty(as));
+          if (close) umma_commit(ROLE == 0 ? rg.gfull(tb) : rg.cfull(tb));
+        }
+        first = 1;
         if (close) {
-          gphase ^= 1u << gb;
-          gb ^= 1;
+          tphase ^= 1u << tb;
+          if (++tb == nbuf) tb = 0;
           in_group = 0;
         }
-        if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
-        if (++s == kw) { s = 0; ++r; }
+        if (item_done) { if (++as == a_stages) { as = 0; aphase ^= 1; } }
+        if (++bs == b_stages) { bs = 0; bphase ^= 1; }
+        if (HALO) {                        // next tap: one pixel (64 B = 4 units) to the right, or the start of the next halo row
+          a16 += 4u;
+          if (++sx == kw) { sx = 0; a16 += row_skip; }
+        }
       }
     }
-    cphase ^= 1u << cb;
-    cb ^= 1;
+  }
+  if (STATS && (threadIdx.x & 31) == 0) {
+    long long* o = p.stats + blockIdx.x * 8;
+    if (ROLE == 0) { o[0] = w_t; o[1] = w_a; o[2] = w_b; o[4] = clock64() - t_begin; }
+    else o[3] = w_t;
+  }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void mma32_dispatch(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base) {
+  if (p.stats) {
+    if (p.halo) mma32<ROLE, true, true>(p, e, rg, tmem_base); else mma32<ROLE, false, true>(p, e, rg, tmem_base);
+  } else {
+    if (p.halo) mma32<ROLE, true, false>(p, e, rg, tmem_base); else mma32<ROLE, false, false>(p, e, rg, tmem_base);
   }
 }
 
 // ---------------------------------------------------------------- warps 8..15: promotion (TMEM groups -> register sums) + epilogue
 // warp -> TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter take alternate 32-column
 // chunks, so a thread owns one output pixel and up to 2 x 32 channels of running sums.
-template <int ACT>
+template <int ACT, bool STATS>
 __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base,
                                                  int warp, int lane) {
   const int q = warp & 3, half = (warp - 8) >> 2;
@@ -400,56 +473,80 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
   const int ngroups = (total_steps + e.group - 1) / e.group;
   const int bn = p.block_n;
   const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  const int c0a = half * 32, c0b = (half + 2) * 32;          // this warp's two 32-column chunks
+  const bool has_a = c0a < bn, has_b = c0b < bn;
   int gb = 0, cb = 0;
   uint32_t gphase = 0, cphase = 0;
+  constexpr bool st = STATS;
+  long long w_g = 0, t_store = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     float sum[2][32];
     for (int g = 0; g < ngroups; ++g) {
+      const long long t0 = st ? clock64() : 0;
       mbar_wait(rg.gfull(gb), (gphase >> gb) & 1u);
+      if (st) w_g += clock64() - t0;
       tc_fence_after();
-      const uint32_t t_row = lane_base + (uint32_t)(gb * T32_MAX_N);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c0 = (half + 2 * k) * 32;
-        if (c0 < bn) {
-          uint32_t r[32];
-          tmem_ld32(t_row + (uint32_t)c0, r);
+      const uint32_t t_row = lane_base + (uint32_t)(gb * e.buf_cols);
+      // one 32-column chunk in flight at a time: with both (64 staging registers next to the 64 running sums) ptxas spills
+      // the sums around every tcgen05.ld; the buffer is released before the last chunk's adds
+      {
+        uint32_t r[32];
+        if (has_a) {
+          tmem_ld32(t_row + (uint32_t)c0a, r);
           tmem_ld_wait();
           if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[k][j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[0][j] = __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[k][j] = __fadd_rn(sum[k][j], __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) sum[0][j] = __fadd_rn(sum[0][j], __uint_as_float(r[j]));
+          }
+        }
+        if (has_b) {
+          tmem_ld32(t_row + (uint32_t)c0b, r);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(rg.gempty(gb));               // the buffer is free as soon as its values sit in registers
+        if (has_b) {
+          if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[1][j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[1][j] = __fadd_rn(sum[1][j], __uint_as_float(r[j]));
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(rg.gempty(gb));
       gphase ^= 1u << gb;
-      gb ^= 1;
+      if (++gb == e.nmain) gb = 0;
     }
     // ---- the tile's correction products
     mbar_wait(rg.cfull(cb), (cphase >> cb) & 1u);
     tc_fence_after();
     {
-      const uint32_t t_row = lane_base + (uint32_t)(2 * T32_MAX_N + cb * T32_MAX_N);
+      const uint32_t t_row = lane_base + (uint32_t)((e.nmain + cb) * e.buf_cols);
+      uint32_t r[32];
+      if (has_a) {
+        tmem_ld32(t_row + (uint32_t)c0a, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c0 = (half + 2 * k) * 32;
-        if (c0 < bn) {
-          uint32_t r[32];
-          tmem_ld32(t_row + (uint32_t)c0, r);
-          tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) sum[0][j] = __fmaf_rn(__uint_as_float(r[j]), T32_LO_INV, sum[0][j]);
+      }
+      if (has_b) {
+        tmem_ld32(t_row + (uint32_t)c0b, r);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(rg.cempty(cb));
+      if (has_b) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[k][j] = __fmaf_rn(__uint_as_float(r[j]), T32_LO_INV, sum[k][j]);
-        }
+        for (int j = 0; j < 32; ++j) sum[1][j] = __fmaf_rn(__uint_as_float(r[j]), T32_LO_INV, sum[1][j]);
       }
     }
-    tc_fence_before();
-    mbar_arrive(rg.cempty(cb));
     cphase ^= 1u << cb;
-    cb ^= 1;
+    if (++cb == e.ncorr) cb = 0;
+    const long long t1 = st ? clock64() : 0;
     // ---- bias / activation / residual / store of this tile (same arithmetic as conv_tc.cu's epilogue)
     const int prob = tile / p.tiles_per_prob;
     const int t_in = tile - prob * p.tiles_per_prob;
@@ -473,7 +570,9 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
         epi_chunk<ACT>(p, r, pix, nbase + c0, nlim);
       }
     }
+    if (st) t_store += clock64() - t1;
   }
+  if (st && warp == 8 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = w_g; p.stats[blockIdx.x * 8 + 6] = t_store; }
 }
 
 // ---------------------------------------------------------------- kernel
@@ -493,7 +592,8 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
       if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;      // sempty, pfull: every converter thread
-      if ((i >= 6 * MAX_STAGES + 2 && i < 6 * MAX_STAGES + 4) || i >= 6 * MAX_STAGES + 6)
+      if ((i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) || (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES)) count = 2;   // pempty, bempty: both issuers
+      if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
         count = 32 * T32_EPI_WARPS;                                               // gempty, cempty: every promotion thread
       mbar_init(rg.bar_base + 8u * i, count);
     }
@@ -502,6 +602,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync()), "r"(0u) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rg.tmem_slot()), "r"((uint32_t)TMEM_COLS)
@@ -521,15 +622,20 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // producer / MMA / converter warpgroups give registers away, the two promotion warpgroups take them
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T32_REGS_LOW));
     if (warp == 0) producer32(p, e, rg, &tmA, &tmB);
-    else if (warp == 1) mma32(p, e, rg, tmem_base);
-    else converter32(p, e, rg, (int)threadIdx.x - 64);
+    else if (warp == 1) mma32_dispatch<0>(p, e, rg, tmem_base);
+    else if (warp == 2) mma32_dispatch<1>(p, e, rg, tmem_base);
+    else converter32(p, e, rg, (int)threadIdx.x - 96);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T32_REGS_HIGH));
-    switch (p.act) {
-      case VPS_ACT_RELU: promote_epilogue<VPS_ACT_RELU>(p, e, rg, tmem_base, warp, lane); break;
-      case VPS_ACT_LRELU: promote_epilogue<VPS_ACT_LRELU>(p, e, rg, tmem_base, warp, lane); break;
-      case VPS_ACT_SIGMOID: promote_epilogue<VPS_ACT_SIGMOID>(p, e, rg, tmem_base, warp, lane); break;
-      default: promote_epilogue<VPS_ACT_NONE>(p, e, rg, tmem_base, warp, lane); break;
+    if (p.stats) {     // debugging aid (VPS_CONV_STATS=1): clocks of the generic path only
+      promote_epilogue<-1, true>(p, e, rg, tmem_base, warp, lane);
+    } else {
+      switch (p.act) {
+        case VPS_ACT_RELU: promote_epilogue<VPS_ACT_RELU, false>(p, e, rg, tmem_base, warp, lane); break;
+        case VPS_ACT_LRELU: promote_epilogue<VPS_ACT_LRELU, false>(p, e, rg, tmem_base, warp, lane); break;
+        case VPS_ACT_SIGMOID: promote_epilogue<VPS_ACT_SIGMOID, false>(p, e, rg, tmem_base, warp, lane); break;
+        default: promote_epilogue<VPS_ACT_NONE, false>(p, e, rg, tmem_base, warp, lane); break;
+      }
     }
   }
 
@@ -542,7 +648,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------- fused DCNv1 kernel (same pipeline, sampling warps feed the ring)
-constexpr int DCN32_REGS_LOW = 88, DCN32_REGS_HIGH = 168;      // 256 * 88 + 256 * 168 = 65536
+constexpr int DCN32_REGS_LOW = 80, DCN32_REGS_HIGH = 176;      // 256 * 80 + 256 * 176 = 65536
 __global__ void __launch_bounds__(T32_THREADS, 1)
 dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const Tc32Extra e, const Dcn32Params d) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -558,12 +664,17 @@ dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParam
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
       if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;
-      if ((i >= 6 * MAX_STAGES + 2 && i < 6 * MAX_STAGES + 4) || i >= 6 * MAX_STAGES + 6) count = 32 * T32_EPI_WARPS;
+      if ((i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) || (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES)) count = 2;
+      if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
+        count = 32 * T32_EPI_WARPS;
       mbar_init(rg.bar_base + 8u * i, count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync()), "r"(0u) : "memory");
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rg.tmem_slot()), "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -579,11 +690,12 @@ dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParam
   if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCN32_REGS_LOW));
     if (warp == 0) producer32(p, e, rg, &tmB, &tmB);
-    else if (warp == 1) mma32(p, e, rg, tmem_base);
-    else dcn_gather32(p, e, d, rg, setup_base, (int)threadIdx.x - 64);
+    else if (warp == 1) mma32<0, false, false>(p, e, rg, tmem_base);
+    else if (warp == 2) mma32<1, false, false>(p, e, rg, tmem_base);
+    else dcn_gather32(p, e, d, rg, setup_base, (int)threadIdx.x - 96);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCN32_REGS_HIGH));
-    promote_epilogue<VPS_ACT_NONE>(p, e, rg, tmem_base, warp, lane);
+    promote_epilogue<VPS_ACT_NONE, false>(p, e, rg, tmem_base, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -759,6 +871,12 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   static int group_env = -1;
   if (group_env < 0) { const char* ev = getenv("VPS_TC32_GROUP"); group_env = ev ? atoi(ev) : 1; }
   e.group = group_env < 1 ? 1 : group_env;
+  e.buf_cols = block_n <= 64 ? 64 : 128;
+  // 128-column buffers: long tiles want a third group buffer (slack for the promotion latency), short tiles (1x1 layers
+  // with few K steps) a second correction buffer so that the next tile can start while this one is stored
+  const bool short_tile = p.cin_chunks * ntaps <= 6;
+  e.nmain = block_n <= 64 ? 6 : (short_tile ? 2 : 3);
+  e.ncorr = block_n <= 64 ? 2 : (short_tile ? 2 : 1);
   p.nprob = nprob;
   p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
   p.total_tiles = p.tiles_per_prob * nprob;
@@ -779,6 +897,9 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   VPS_CHECK_ARG(!a->bias || ((uintptr_t)a->bias & 15) == 0, "conv2d_tc32: bias must be 16-byte aligned");
   p.bias = a->bias; p.cout = a->cout; p.act = a->act; p.slope = a->slope; p.out_scale = a->out_scale;
   if (a->res.ptr) VPS_CHECK_ARG(a->res.h == a->y.h && a->res.w == a->y.w, "conv2d_tc32: residual geometry");
+  static int stats_env = -1;
+  static long long* stats_buf = nullptr;
+  if (stats_env < 0) { const char* ev = getenv("VPS_CONV_STATS"); stats_env = ev ? atoi(ev) : 0; }
   p.stats = nullptr;
   if (p.total_tiles == 0) return VPS_OK;
 
@@ -816,6 +937,11 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
     smem_set = true;
   }
   const int grid = p.total_tiles < g_num_sms32 ? p.total_tiles : g_num_sms32;
+  if (stats_env) {   // debugging aid: per-role barrier-wait clocks, printed after a device sync (never on in production)
+    if (!stats_buf) cudaMalloc(&stats_buf, sizeof(long long) * 8 * 1024);
+    cudaMemsetAsync(stats_buf, 0, sizeof(long long) * 8 * grid, (cudaStream_t)stream);
+    p.stats = stats_buf;
+  }
   static int pdl_env = -1;
   if (pdl_env < 0) { const char* ev = getenv("VPS_PDL"); pdl_env = ev ? atoi(ev) : 1; }
   cudaLaunchConfig_t cfg = {};
@@ -828,6 +954,19 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_tc32_kernel, tmA, tmB, p, e);
   if (le != cudaSuccess) { vps::set_error("conv2d_tc32: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
   VPS_CUDA_LAST("conv_igemm_tc32_kernel");
+  if (stats_env) {
+    static long long h[8 * 1024];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, stats_buf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    double m[8] = {0};
+    for (int i = 0; i < grid; ++i) for (int j = 0; j < 8; ++j) m[j] += (double)h[i * 8 + j] / grid;
+    const int tiles_cta = (p.total_tiles + grid - 1) / grid;
+    const int steps = ntaps * p.cin_chunks;
+    fprintf(stderr, "conv_tc32 stats %dx%d s%d %d->%d @%dx%d halo=%d bn=%d G=%d stages a%d b%d tiles/cta %d steps/tile %d | clk/CTA total %.0f "
+            "(%.0f per step) | mma waits: group-buf %.0f planes %.0f weights %.0f corr-buf %.0f | promo: wait gfull %.0f store %.0f\n",
+            a->kh, a->kw, a->sh, a->cin, a->cout, a->oh, a->ow, p.halo, block_n, e.group, p.a_stages, p.b_stages, tiles_cta, steps, m[4],
+            m[4] / (tiles_cta * steps), m[0], m[1], m[2], m[3], m[5], m[6]);
+  }
   return VPS_OK;
 }
 
@@ -875,6 +1014,9 @@ extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offse
   e.rows = BLOCK_M; e.dcn = 1;
   e.plane_bytes = BLOCK_M * 64; e.stage_bytes = 0; e.nk_last = 2;
   e.b_plane_bytes = block_n * 64;
+  e.buf_cols = block_n <= 64 ? 64 : 128;
+  e.nmain = block_n <= 64 ? 6 : 3;
+  e.ncorr = block_n <= 64 ? 2 : 1;
   p.a_box_bytes = 0; p.a_stage_bytes = T32_PLANES * e.plane_bytes;
   p.a_stages = 3;
   {

@@ -259,9 +259,10 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float t = v[j];
-    if (ACT == VPS_ACT_RELU) t = fmaxf(t, 0.f);
-    else if (ACT == VPS_ACT_LRELU) t = t > 0.f ? t : t * p.slope;
-    else if (ACT == VPS_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+    const int act = ACT < 0 ? p.act : ACT;          // ACT = -1: decided at run time (instrumented debugging build only)
+    if (act == VPS_ACT_RELU) t = fmaxf(t, 0.f);
+    else if (act == VPS_ACT_LRELU) t = t > 0.f ? t : t * p.slope;
+    else if (act == VPS_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
     v[j] = t * p.out_scale;
   }
   if (has_res && p.res_after_act) add_res();
