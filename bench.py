@@ -5,8 +5,12 @@
   python bench.py --impl reference --gpus N --steps K ...  # reference arm: the oracle port on the host CPU cores
 
 One step = one `simple_test` call = one frame pair -> one panoptic frame.  Prints ONE JSON line (rank 0).
+The headline (`value`, `e2e`, `roofline`) is measured in the PARITY precision "tc32" (fp32 activations, tcgen05 with split
+fp16 operands: label maps / ids identical to the oracle, tests/test_gpu_e2e.py, tests/test_gpu_fullsize.py); the bf16
+fast mode (one tensor-core pass, ~0.99 label agreement) is timed in the same run and reported under `fast_mode`.
   value      : pairs/s over ONE device-timed region (CUDA events) of K steps through the public clip loop
                (vps_b200.runner.ClipRunner), inputs already resident in HBM, max over ranks, summed over ranks
+  --workload viper : BASELINE config 4 -- 30-frame 1088x1920 clips (1080 padded to 1088), one clip stream per GPU
   e2e        : the same region with HOST (pinned) frames: H2D of both frames and D2H of the label maps of every step
                inside the timed region
   sequential_ms_per_pair : one pair at a time, L2 flushed in between (latency)
@@ -118,31 +122,27 @@ def time_oracle(model, H, W, reps, threads):
     return times
 
 
-def pick_sample(model, threads, per_step_budget_s):
-    """largest sample size (64x128 ... 1024x2048) whose predicted single-pair time stays within the budget"""
-    sizes = [((64, 128), 1.0 / 256), ((128, 256), 1.0 / 64), ((256, 512), 1.0 / 16), ((512, 1024), 0.25), ((1024, 2048), 1.0)]
-    time_oracle(model, 64, 128, 1, threads)                       # warm-up (lazy inits)
-    (H0, W0), frac = sizes[0]
-    t = time_oracle(model, H0, W0, 1, threads)[0]
-    size = (H0, W0)
-    for (hh, ww), fr in sizes[1:]:
-        if t * 4 * 1.3 > per_step_budget_s:
-            break
-        t = time_oracle(model, hh, ww, 1, threads)[0]
-        size, frac = (hh, ww), fr
-    return size, frac, t
+# The CPU arms time the oracle on ONE fixed sample size (deterministic from run to run): a 512x1024 pair = 1/4 of the
+# 1024x2048 area, ~5-10 s per pair on 32 host threads, scaled by area (the dense work is linear in pixels; the fixed
+# per-frame head cost makes the sample slightly pessimistic for the CPU).  VPS_BENCH_CPU_SAMPLE=HxW overrides it
+# (1024x2048 = the full workload, ~30-40 s per pair).
+def cpu_sample():
+    v = os.environ.get("VPS_BENCH_CPU_SAMPLE", "512x1024").lower().split("x")
+    return int(v[0]), int(v[1])
 
 
-def cpu_baseline(budget_s=15.0):
-    """Oracle on the host cores on a bounded sample: one frame pair at the largest size whose predicted time fits the
-    budget, scaled to 1024x2048-equivalent pairs/s by the area ratio (the dense work is linear in pixels; the fixed
-    per-frame head cost makes small samples slightly pessimistic for the CPU)."""
+def cpu_baseline():
+    """Oracle on the host cores on the fixed bounded sample: 1 warm-up + 2 timed pairs."""
     threads = host_threads()
     m = oracle_model()
-    size, frac, t = pick_sample(m, threads, budget_s)
+    Hs, Ws = cpu_sample()
+    frac = Hs * Ws / float(H_FULL * W_FULL)
+    time_oracle(m, 64, 128, 1, threads)
+    ts = time_oracle(m, Hs, Ws, 3, threads)[1:]
+    t = float(np.mean(ts))
     return {"value": frac / t, "unit": "pairs/s (1024x2048-equivalent)", "cores": threads, "kind": "port",
-            "sample": "oracle simple_test, 1 pair at %dx%d (%.3g of the 1024x2048 area) in %.2fs, scaled by area; fp32, torch CPU ops"
-                      % (size[0], size[1], frac, t)}
+            "sample": "oracle simple_test, 2 timed pairs at %dx%d (%.3g of the 1024x2048 area) in %.2f s each, scaled by area; "
+                      "fp32, torch CPU ops" % (Hs, Ws, frac, t)}
 
 
 def run_reference_arm(args):
@@ -150,11 +150,13 @@ def run_reference_arm(args):
     (mmcv 0.2.14 + THC extensions, hard .cuda() calls), so this is the oracle port (kind 'port').
     Each step = one frame pair at a bounded sample size chosen so that a step takes a few seconds."""
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if rank != 0:            # no process group is created in this arm: the other ranks have nothing to do and exit at once
         return
     threads = host_threads()
     m = oracle_model()
-    (Hs, Ws), frac, _ = pick_sample(m, threads, per_step_budget_s=float(os.environ.get("VPS_BENCH_STEP_BUDGET_S", "10.0")))
+    Hs, Ws = cpu_sample()
+    frac = Hs * Ws / float(H_FULL * W_FULL)
+    time_oracle(m, 64, 128, 1, threads)                           # lazy inits
     times = time_oracle(m, Hs, Ws, args.warmup + args.steps, threads)[args.warmup:]
     t = float(np.mean(times))
     v = frac / t
@@ -162,7 +164,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / frac, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "FuseTrack inference, synthetic 2-frame 1024x2048 pair, random-init (synthetic set C) weights",
+            "config": {"workload": "FuseTrack inference, synthetic 2-frame 1024x2048 pair, random-init (synthetic set C) weights (CPU arm: fixed bounded sample, see `sample`)",
                        "sample": sample},
             "cpu_baseline": {"value": v, "unit": "pairs/s (1024x2048-equivalent)", "cores": threads, "kind": "port",
                              "sample": "oracle simple_test, %d steps; %s" % (args.steps, sample)},
@@ -184,21 +186,67 @@ def build_product(precision, device):
     return det
 
 
+def stock_pytorch_r50fpn(dev, H, W, flush):
+    """Context (BASELINE.md section 3 / SURVEY 8d "the real bar to beat"): the SAME ResNet-50-FPN math as stock PyTorch
+    modules (the oracle's, i.e. test infrastructure -- not the product) on this GPU through cuDNN: fp32 (TF32 off), TF32 and
+    bf16 channels_last autocast, both frames as a batch of 2, median of 5 with L2 flush."""
+    from oracle.model import PanopticFuseTrack as Oracle
+    from vps_b200.synth import make_weights
+    m = Oracle()
+    make_weights(m, "C", 0)
+    net = torch.nn.Sequential()
+    bb, neck = m.backbone.to(dev).eval(), m.neck.to(dev).eval()
+    x = torch.randn(2, 3, H, W, device=dev)
+    out = {}
+
+    def run(tag, xin, ctx):
+        with torch.no_grad(), ctx:
+            for _ in range(2):
+                neck(bb(xin))
+            torch.cuda.synchronize()
+            ts = []
+            for i in range(5):
+                flush.fill_(i)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); neck(bb(xin)); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[2]
+        out[tag] = {"ms": round(ms, 3), "tflops": round(GFLOP_R50FPN_PAIR * (H * W) / float(H_FULL * W_FULL) / ms, 1)}
+
+    import contextlib
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    run("fp32", x, contextlib.nullcontext())
+    torch.backends.cudnn.allow_tf32 = True
+    run("tf32", x, contextlib.nullcontext())
+    bb.to(memory_format=torch.channels_last); neck.to(memory_format=torch.channels_last)
+    run("bf16_channels_last", x.contiguous(memory_format=torch.channels_last), torch.autocast("cuda", dtype=torch.bfloat16))
+    out["what"] = "oracle ResNet-50 + FPN modules (stock torch.nn / cuDNN, eager), 2 frames %dx%d as one batch; algorithmic 1158.4 GFLOP" % (H, W)
+    return out
+
+
 def run_gpu_arm(args):
     from vps_b200 import ops
     from vps_b200 import parallel as P
     rank, local, world = P.env_world()
+    # the CPU leg (rank 0, N = 1 only) runs BEFORE the process group exists: no GPU spins in a collective meanwhile
+    cpu_leg = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_leg = cpu_baseline()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     P.init("nccl", dev)
-    H, W = args.height, args.width
+    viper = args.workload == "viper"
+    H, W = (1088, 1920) if viper else (args.height, args.width)
     det = build_product(args.precision, dev)
     det.label_dtype = torch.uint8                    # the reference's collector casts both maps to uint8 (test_vpq.py:52-56)
     NPAIR = 4                                        # 4 distinct pairs = 201 MB of fp32 frames (> 126 MB L2)
     host = [(a.pin_memory(), b.pin_memory()) for a, b in synth_pairs(NPAIR, H, W, seed=100 + rank)]
     devp = [(a.to(dev), b.to(dev)) for a, b in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    CLIP = 30                                        # Cityscapes-VPS clip length: tracker memory resets every 30 frames
+    CLIP = 30                                        # clip length (Cityscapes-VPS and the VIPER workload): tracker memory resets
 
     def step(i):
         iid = 10000 * (1 + rank) + 1 + (i % CLIP)
@@ -263,6 +311,25 @@ def run_gpu_arm(args):
     h2d_gbps = 8 * 3 * H * W * 4 / (hs.elapsed_time(he) * 1e-3) / 1e9
     sampler.stop_flag = True
     seq_ms = timed(min(args.steps, 5), args.warmup)               # one pair at a time, L2 flushed: latency of a pair
+    # ---- the bf16 fast mode (one tensor-core pass; NOT the reference's precision) in the same run, same regions
+    fast = None
+    if args.precision == "tc32" and not args.no_fast_mode:
+        det.precision = "bf16"
+        for i in range(3):
+            step(i)
+        region(5, 0, True)
+        region(2, 0, False)
+        torch.cuda.synchronize()
+        P.barrier()
+        f_ms = region(args.steps, args.warmup + 5, True)
+        P.barrier()
+        f_e2e = region(args.steps, args.warmup + 5 + args.steps, False)
+        f_dev, f_e = [v / 1e3 for v in P.max_over_ranks([f_ms, f_e2e], dev)]
+        fast = {"precision": "bf16", "value": world * args.steps / f_dev, "e2e": world * args.steps / f_e, "unit": "pairs/s",
+                "ms_per_step": 1e3 * f_dev / args.steps,
+                "parity": "bf16 operands, one tcgen05 pass: label agreement with the oracle 0.99 (semantic 0.9945 / panoptic 0.9896 "
+                          "at 1024x2048, tests/test_gpu_fullsize.py) -- lower precision than the reference, reported for context"}
+        det.precision = args.precision
     # ---- SURVEY 8f rank 1 (the step after the path): get_unified_pan_result on the GPU, timed alone on a real result
     from vps_b200.postproc import PanUnifier
     unifier = PanUnifier()
@@ -320,16 +387,36 @@ def run_gpu_arm(args):
             a = agg.setdefault(name, [0.0, 0.0, 0])
             a[0] += s.elapsed_time(e); a[1] += fl; a[2] += 1
         tc_ms, tc_fl, tc_n = 0.0, 0.0, 0
-        for kname in ("vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_conv2d_tc32", "vps_conv2d_tc32_multi"):
+        tc32 = args.precision == "tc32"
+        names = ("vps_conv2d_tc32", "vps_conv2d_tc32_multi", "vps_deform_conv_tc32") if tc32 else \
+                ("vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_deform_conv_tc")
+        for kname in names:
             a_ = agg.get(kname, [0.0, 0.0, 0])
             tc_ms, tc_fl, tc_n = tc_ms + a_[0], tc_fl + a_[1], tc_n + a_[2]
         pk = peaks()
         if tc_ms > 0:
             ach = tc_fl / (tc_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "conv_igemm_tc_kernel (all %d launches of a step)" % (tc_n // 2),
-                    "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
-                    "peak_source": pk["src"] + " bf16_tflops_sustained",
-                    "flops_per_step": tc_fl / 2, "ms_per_step": tc_ms / 2}
+            passes = 3 if tc32 else 1
+            # DRAM traffic of the same kernels over one step, from the committed ncu pass (profiles/, see its README)
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get("tc32" if tc32 else "bf16")
+                except Exception:
+                    traffic = None
+            roof = {"bound": "tensor",
+                    "kernel": ("conv_igemm_tc32_kernel + dcn_igemm_tc32_kernel" if tc32 else "conv_igemm_tc_kernel + dcn_igemm_tc_kernel")
+                              + " (all %d launches of a step)" % (tc_n // 2),
+                    "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": traffic,
+                    "peak_source": pk["src"] + " bf16_tflops_sustained (cuBLAS bf16, back to back)",
+                    "flops_per_step": tc_fl / 2, "ms_per_step": tc_ms / 2,
+                    "tensor_passes": passes,
+                    "tensor_pipe_frac": passes * ach / pk["tf_sus"],
+                    "note": "achieved = ALGORITHMIC conv FLOPs (2*MAC of the fp32 layer) / summed kernel time; the parity precision "
+                            "executes 3 f16 tensor-core products per algorithmic MAC (fp16 value + scaled residual split of both "
+                            "operands), so frac <= 1/3 by construction and tensor_pipe_frac = 3 * frac is the pipe utilisation"
+                            if tc32 else "achieved = algorithmic conv FLOPs / summed kernel time"}
         total_ms = sum(a[0] for a in agg.values())
         breakdown = {k: {"ms_per_step": round(a[0] / 2, 3), "share": round(a[0] / total_ms, 4), "calls": a[2] // 2}
                      for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
@@ -340,16 +427,20 @@ def run_gpu_arm(args):
         bytes_out = 2 * H * W * det.label_dtype.itemsize
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "FuseTrack inference, synthetic 2-frame %dx%d pair, random-init (synthetic set C) weights, "
-                                       "1 clip stream per GPU" % (H, W),
+                "dtype": {"tc32": "f32 (tcgen05: 3 split-f16 products per MAC, fp32 accumulate promoted to RN register sums)",
+                          "bf16": "bf16", "fp32": "f32 (CUDA cores)"}[args.precision], "data": "synthetic",
+                "config": {"workload": ("VIPER-shape streaming inference, synthetic 30-frame 1088x1920 clips (1080 padded to 1088), " if viper else
+                                        "FuseTrack inference, synthetic 2-frame %dx%d pair, " % (H, W)) +
+                                       "random-init (synthetic set C) weights, 1 clip stream per GPU",
+                           "precision": args.precision,
                            "parallelism": "clip-sharded replicas x%d, no data-path collective" % world,
                            "l2": "4 rotating input pairs (201 MB of fp32 frames > 126 MB L2) in both timed regions, steps are "
                                  "pipelined so no flush between them; sequential_ms_per_pair flushes 256 MiB between pairs",
                            "pipelining": "static part of pair i+1 (second CUDA-graph instance, side stream) overlaps pair i's "
                                          "tracker/mask/fusion tail; max(W,5) + 2 untimed runner steps precede the timed regions",
                            "labels": "uint8 label maps (same values as the reference's int64; its collector casts to uint8)",
-                           "precision_note": "bf16 operands / fp32 accumulate on tcgen05; fp32 parity mode via --precision fp32"},
+                           "precision_note": "tc32 = the parity precision (label maps / ids identical to the oracle: tests/test_gpu_e2e.py, "
+                                             "tests/test_gpu_fullsize.py); --precision bf16 = fast mode, --precision fp32 = CUDA-core debugging twin"},
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
                         "h2d_gbps_measured": round(h2d_gbps, 2)},
                 "gpu_launches": int(launches), "clocks": clocks,
@@ -392,8 +483,15 @@ def run_gpu_arm(args):
                 line["r50fpn_roofline"] = {"achieved": ach, "peak": peaks()["tf_sus"], "unit": "TFLOP/s",
                                            "frac": ach / peaks()["tf_sus"], "ms": r50_ms, "eager_instrumented_ms": scopes["r50fpn"][0],
                                            "note": "stage captured as its own CUDA graph, median of 5 replays with L2 flush; algorithmic 1158.4 GFLOP/pair"}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+        if fast is not None:
+            line["fast_mode"] = fast
+        if cpu_leg is not None:
+            line["cpu_baseline"] = cpu_leg
+        if world == 1 and not args.no_stock:
+            try:
+                line["stock_pytorch_r50fpn"] = stock_pytorch_r50fpn(dev, H, W, flush)
+            except Exception as ex:          # context only: never fail the bench on it
+                line["stock_pytorch_r50fpn"] = {"unavailable": repr(ex)[:200]}
         print(json.dumps(line))
     P.barrier()
     if world > 1:
@@ -411,6 +509,10 @@ def main():
     ap.add_argument("--height", type=int, default=H_FULL)
     ap.add_argument("--width", type=int, default=W_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the bf16 fast-mode leg")
+    ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch (cuDNN) ResNet-50-FPN context leg")
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "viper"],
+                    help="pairs = BASELINE config 2 (1024x2048 pairs); viper = config 4 (30-frame 1088x1920 clips, one per GPU)")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs under ncu only (numbers are not bench values)")
     ap.add_argument("--profile-out", default="", help="write per-call device timings of one instrumented step (JSON lines)")
     args = ap.parse_args()

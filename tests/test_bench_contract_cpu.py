@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    env = dict(os.environ, VPS_BENCH_STEP_BUDGET_S="1.0")           # keep the sample at the smallest size for the test
+    env = dict(os.environ, VPS_BENCH_CPU_SAMPLE="64x128")           # keep the sample small for the test (default: 512x1024)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]

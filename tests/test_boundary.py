@@ -55,6 +55,40 @@ def test_reference_config_loads_unmodified_and_builds():
     assert det.class_mapping == {i: 10 + i for i in range(1, 9)}
 
 
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference tree not mounted")
+def test_b200_classes_build_through_the_reference_registries():
+    """SURVEY 8b, second route: overwrite mmdet.models.registry.*.module_dict[name] with the B200 classes and build the
+    detector through the REFERENCE's own build_detector / build_from_cfg from the unmodified config.  Runs in a
+    subprocess: importing the reference on this mmcv-less CPU box needs process-wide stubs (tests/golden/ref_import.py)."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys
+sys.path.insert(0, %r)
+from tests.golden.ref_import import REF, setup
+M = setup()                                  # the reference's mmdet.models (its registries now hold ITS classes)
+import mmdet.models.registry as RR
+import mmdet.models.builder as RB
+ref_cls = RR.DETECTORS.get('PanopticFuseTrack')
+assert ref_cls is not None and ref_cls.__module__.startswith('mmdet.')
+import vps_b200
+from vps_b200.registry import install_into_reference
+done = install_into_reference(RR)
+assert ('DETECTORS', 'PanopticFuseTrack') in done and ('BACKBONES', 'ResNet') in done and len(done) >= 12
+from vps_b200.config import Config
+cfg = Config.fromfile(os.path.join(REF, 'configs/cityscapes/fusetrack.py'))
+cfg.model['pretrained'] = None
+det = RB.build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)      # the reference's builder
+assert type(det).__module__ == 'vps_b200.detector', type(det)
+for name in ('backbone', 'neck', 'extra_neck', 'panopticFPN', 'rpn_head', 'bbox_head', 'track_head', 'mask_head'):
+    assert type(getattr(det, name)).__module__.startswith('vps_b200.'), name
+assert len(det.state_dict()) == 629
+print('OK', len(done))
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-3000:]
+
+
 def _plain(x):
     if isinstance(x, dict):
         return {k: _plain(v) for k, v in x.items()}

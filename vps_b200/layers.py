@@ -85,6 +85,8 @@ class StemConv7x7s2:
         if y is None:
             y = empty_nhwc(n, oh, ow, self.cout, out_dtype or x.dtype, x.device)
         # the 4x4/pad-2 conv yields (h/2 + 1) rows; the stride-2 conv defines only the first oh x ow of them
+        if ops.PROFILE is not None:
+            ops._NOTE["flops_alg"] = 2 * n * oh * ow * self.cout * self.cin * 49
         ops.conv2d(xs, self.s2d.pk, y, stride=1, pad=2, act=self.act if act is None else act, slope=self.s2d.slope,
                    oh=oh, ow=ow, use_tc=True)
         return y

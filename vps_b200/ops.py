@@ -229,7 +229,9 @@ def conv2d(x, pw, y, stride=1, pad=0, act=ACT_NONE, slope=0.1, res=None, res_aft
     if use_tc is None:
         use_tc = x.dtype == torch.bfloat16
     if PROFILE is not None:
-        _NOTE["flops"] = 2 * x.shape[0] * a.oh * a.ow * pw.cout * pw.cin * a.kh * a.kw
+        # algorithmic FLOPs of the layer: a caller that runs a re-shaped form (the 7x7/s2 stems as 4x4/s1 over
+        # space-to-depth input) passes the original layer's count in _NOTE["flops_alg"]
+        _NOTE["flops"] = _NOTE.pop("flops_alg", None) or 2 * x.shape[0] * a.oh * a.ow * pw.cout * pw.cin * a.kh * a.kw
         _NOTE["tag"] = "%dx%d s%d %d->%d @%dx%d" % (a.kh, a.kw, a.sh, pw.cin, pw.cout, a.oh, a.ow)
     if use_tc and x.dtype == torch.float32:
         a.w = pw.tc32().data_ptr()

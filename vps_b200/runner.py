@@ -51,13 +51,14 @@ class ClipRunner:
         return bufs[0], bufs[1], ev
 
     def _host_buf(self, i, like):
-        while len(self._out) <= i % self.depth:
+        k = i % (self.depth + 1)
+        while len(self._out) <= k:
             self._out.append(None)
-        buf = self._out[i % self.depth]
+        buf = self._out[k]
         if buf is None or buf[0].shape != like.shape or buf[0].dtype != like.dtype:
             buf = (torch.empty(like.shape, dtype=like.dtype).pin_memory(), torch.empty(like.shape, dtype=like.dtype).pin_memory(),
                    torch.cuda.Event())
-            self._out[i % self.depth] = buf
+            self._out[k] = buf
         return buf
 
     def _stage(self, pair, resident):
@@ -69,8 +70,10 @@ class ClipRunner:
     def run(self, pairs, metas, resident=False, prefetch=True):
         """pairs: iterable of (img, ref_img) pinned host tensors [1,3,H,W] fp32 (device tensors if `resident`); metas:
         matching img_meta dicts.  Yields (bbox_results, segm_results, pano_results) per pair, in order;
-        pano_results['panoptic_outputs'] and ['fcn_outputs'] are HOST tensors (pinned ring buffers, valid until `depth`
-        further results were produced).  With `prefetch` the tracker-independent static part of pair i+1
+        pano_results['panoptic_outputs'] and ['fcn_outputs'] are HOST tensors in a ring of depth + 1 pinned buffers: the
+        download of pair i + depth + 1 reuses the slot of pair i and is issued right before result i + depth is yielded, so a
+        result stays valid while the next `depth - 1` results are consumed (depth = 2: the previous result may still be
+        read while the current one is processed); clone to keep results longer.  With `prefetch` the tracker-independent static part of pair i+1
         (`det.prefetch`) is enqueued before pair i's data-dependent tail runs, so the two overlap."""
         main = torch.cuda.current_stream(self.dev)
         it = iter(zip(pairs, metas))
@@ -106,11 +109,12 @@ class ClipRunner:
             hp, hs, hev = self._host_buf(i, pano)
             h2 = None
             if p2 is not None:
-                while len(self._out2) <= i % self.depth:
+                k2 = i % (self.depth + 1)
+                while len(self._out2) <= k2:
                     self._out2.append(None)
-                h2 = self._out2[i % self.depth]
+                h2 = self._out2[k2]
                 if h2 is None or h2.shape != p2.shape:
-                    h2 = self._out2[i % self.depth] = torch.empty(p2.shape, dtype=torch.uint8).pin_memory()
+                    h2 = self._out2[k2] = torch.empty(p2.shape, dtype=torch.uint8).pin_memory()
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(done)
                 hp.copy_(pano, non_blocking=True)
