@@ -333,6 +333,10 @@ int64_t vps_unify_pan_ws_bytes(void);
 int vps_unify_pan(const void* seg, const void* pan, int label_bytes, int H, int W, const int32_t* cls_ind,
                   const int32_t* obj_id, int k, int id_last_stuff, int stuff_area_limit, uint8_t* out, void* ws,
                   int64_t ws_bytes, void* stream);
+/* 1 if the last vps_unify_pan call on `ws` met a panoptic instance id without a cls_ind entry (the reference raises
+ * IndexError there, cityscapes_vps.py:197); synchronises `stream` */
+int vps_unify_pan_error(const void* ws, void* stream);
+int64_t vps_unify_pan_error_offset(void);   /* byte offset of that flag (int32) inside ws, for asynchronous read-back */
 
 /* ---- pixel-level step of the VPQ evaluator (tools/eval_vpq.py:138-145) --------------------------
  * np.unique(gt.astype(uint64) * offset + pred, return_counts=True) over a tube of id maps (npix = nframes*H*W, device
@@ -343,9 +347,11 @@ int64_t vps_tube_confusion_ws_bytes(int64_t npix);
 int vps_tube_confusion(const uint32_t* gt_ids, const uint32_t* pred_ids, int64_t npix, uint64_t offset, uint64_t* pairs_out,
                        uint32_t* counts_out, int* nruns_dev, void* ws, int64_t ws_bytes, void* stream);
 int vps_rgb_to_id(const uint8_t* rgb, int64_t npix, uint32_t* ids, void* stream);
-/* segment ids of a unified 3-channel result [npix,3] (vps_unify_pan): 1000 * semantic + track channel + 1, VOID (semantic
- * 255) -> 0 -- the keying of converter_2ch_track_core (tools/dataset/cityscapes_vps.py:104-111) without its random colours */
-int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, uint32_t* ids, void* stream);
+/* segment ids of a unified 3-channel result [npix,3] (vps_unify_pan): the segmentation converter_2ch_track_core
+ * (tools/dataset/cityscapes_vps.py:104-140) produces through panopticapi's colours -- ONE segment per stuff category
+ * (semantic < num_stuff: id 1000 * semantic + 1, whatever the track channel holds), one per (thing category, track) key
+ * (id 1000 * semantic + track + 1), VOID (semantic 255) -> 0 */
+int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, int num_stuff, uint32_t* ids, void* stream);
 
 #ifdef __cplusplus
 }

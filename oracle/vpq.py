@@ -148,11 +148,14 @@ def pq_average(stat, categories, isthing=None):
     return {"pq": pq / n, "sq": sq / n, "rq": rq / n, "n": n}, per_class
 
 
-def segments_from_pan2ch(pan_2ch):
-    """numpy counterpart of vps_b200.vpq.segments_from_pan2ch (keying of converter_2ch_track_core,
-    tools/dataset/cityscapes_vps.py:96-131, without its random colours): returns (ids uint32 [H,W], segments)."""
+def segments_from_pan2ch(pan_2ch, num_stuff=11):
+    """numpy counterpart of vps_b200.vpq.segments_from_pan2ch: the segmentation converter_2ch_track_core produces
+    (tools/dataset/cityscapes_vps.py:96-140) -- one segment per stuff category (panopticapi's IdGenerator returns the
+    category's fixed colour for every key of a stuff class), one per (thing category, track) key -- with deterministic ids
+    instead of colours: returns (ids uint32 [H,W], segments)."""
     p = np.asarray(pan_2ch).astype(np.uint32)
-    ids = np.where(p[..., 0] == 255, 0, 1000 * p[..., 0] + p[..., 2] + 1).astype(np.uint32)
+    sem, trk = p[..., 0], p[..., 2]
+    ids = np.where(sem == 255, 0, 1000 * sem + np.where(sem < num_stuff, 0, trk) + 1).astype(np.uint32)
     segs = []
     for i, a in zip(*np.unique(ids, return_counts=True)):
         if i == VOID:

@@ -1,8 +1,9 @@
 """Golden vectors for SURVEY 8f rank 1b (2-channel -> PNG/JSON converter): runs the REFERENCE's own
 `converter_2ch_track_core` (/root/reference/tools/dataset/cityscapes_vps.py:96-158, imported unmodified) on seeded synthetic
-3-channel frames.  panopticapi (the colour generator) is not vendored in the reference: a stand-in `IdGenerator` hands out
-distinct colours (fixed colour per stuff category, fresh colour per thing request) so the run is reproducible; ids are
-therefore compared modulo a bijection.  Output: tests/golden/writer_frames.npz + .json.
+semantic / panoptic maps chained through the reference's own `get_unified_pan_result` (:162-226).  panopticapi (the colour
+generator) is not vendored in the reference: a stand-in `IdGenerator` with panopticapi's contract (the category's fixed
+colour for a stuff category, a fresh colour per request for a thing category) makes the run reproducible; ids are therefore
+compared modulo a bijection.  Output: tests/golden/writer_frames.npz + .json.
 Run in the build container only:  python tests/golden/make_writer_golden.py"""
 import json
 import os
@@ -33,24 +34,19 @@ def rgb2id(color):
     return int(c[0] + 256 * c[1] + 65536 * c[2])
 
 
-def synth_clip(rng, nfr, H, W):
-    frames = []
-    base = rng.integers(0, 11, size=((H + 15) // 16, (W + 15) // 16)).repeat(16, 0).repeat(16, 1)[:H, :W]
-    inst = [(int(rng.integers(11, 19)), int(rng.integers(6, H // 2)), int(rng.integers(6, W // 2)), int(rng.integers(0, H // 2)),
-             int(rng.integers(0, W // 2)), int(rng.integers(1, 200))) for _ in range(7)]
+def synth_clip(Cvps, rng, nfr, H, W):
+    """frames as the path produces them: seeded semantic / panoptic maps through the REFERENCE's own get_unified_pan_result
+    (so stuff pixels carry their pan value in the track channel, demoted thing regions carry 0, small stuff becomes VOID
+    with a leftover track value, duplicate track ids are re-numbered), plus a VOID band."""
+    from make_unify_golden import synth_frame
+    segs, pans, clss, objs = [], [], [], []
     for f in range(nfr):
-        p = np.zeros((H, W, 3), np.uint8)
-        p[..., 0] = base
-        p[:5, :, 0] = 255                                              # VOID band
-        for rank, (c, h, w, y, x, trk) in enumerate(inst):
-            if (f + rank) % 4 == 3:
-                continue                                               # instance absent in this frame
-            yy, xx = min(y + f, H - h), min(x + 2 * f, W - w)
-            p[yy:yy + h, xx:xx + w, 0] = c
-            p[yy:yy + h, xx:xx + w, 1] = rank + 1
-            p[yy:yy + h, xx:xx + w, 2] = trk
-        frames.append(p)
-    return frames
+        seg, pan, cls, obj = synth_frame(rng, H, W, 9, with_255=(f == 2))
+        obj = (obj % 5) + 1 if f % 2 else obj            # some track ids recur across frames
+        segs.append(seg); pans.append(pan); clss.append(cls); objs.append(obj)
+    names = ["f%d" % i for i in range(nfr)]
+    out = Cvps.get_unified_pan_result(None, segs, pans, clss, obj_ids=objs, stuff_area_limit=300, names=names)
+    return [out[n] for n in names]
 
 
 def main():
@@ -61,7 +57,7 @@ def main():
     Cvps = import_reference()
     categories = {i: {"id": i, "isthing": 1 if i >= 11 else 0} for i in range(19)}
     rng = np.random.default_rng(99)
-    frames = synth_clip(rng, 6, 64, 96)
+    frames = synth_clip(Cvps, rng, 6, 96, 160)
     ann, pans = Cvps.converter_2ch_track_core(None, 0, frames, StandInIdGenerator(categories))
     out = {"nframes": np.int64(len(frames))}
     for i, (fr, pf) in enumerate(zip(frames, pans)):

@@ -59,3 +59,20 @@ def test_unify_no_instances_and_cpu_inputs_fail(cuda):
     assert np.array_equal(got, ref)
     with pytest.raises(RuntimeError):
         PanUnifier()(torch.from_numpy(seg), torch.from_numpy(seg), np.zeros(0, np.int64))
+
+
+def test_unify_flags_instance_id_without_class(cuda):
+    """a panoptic id beyond len(cls_ind): the reference raises IndexError (cityscapes_vps.py:197); PanUnifier.check() does too"""
+    import numpy as np
+    from vps_b200.postproc import PanUnifier
+    H, W = 64, 96
+    seg = torch.zeros(H, W, dtype=torch.uint8, device="cuda")
+    pan = torch.zeros(H, W, dtype=torch.uint8, device="cuda")
+    pan[10:20, 10:30] = 11 + 3                      # instance j = 3, but only 2 classes are given
+    u = PanUnifier(stuff_area_limit=16)
+    u(seg, pan, np.array([1, 2]), np.array([0, 1]))
+    with pytest.raises(IndexError):
+        u.check()
+    pan[10:20, 10:30] = 11 + 1
+    u(seg, pan, np.array([1, 2]), np.array([0, 1]))
+    u.check()

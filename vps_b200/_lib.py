@@ -50,6 +50,7 @@ def lib():
         _lib.vps_packed_tc_bytes.restype = C.c_int64
         _lib.vps_packed_tc32_bytes.restype = C.c_int64
         _lib.vps_unify_pan_ws_bytes.restype = C.c_int64
+        _lib.vps_unify_pan_error_offset.restype = C.c_int64
         _lib.vps_tube_confusion_ws_bytes.restype = C.c_int64
         _lib.vps_tube_confusion_ws_bytes.argtypes = [C.c_int64]
         _lib.vps_add_launch_count.restype = None
@@ -76,5 +77,5 @@ EXPORTS = [
     "vps_roi_align", "vps_sort_desc", "vps_rpn_decode", "vps_nms", "vps_nms_batch", "vps_sigmoid_flat", "vps_gather_rows",
     "vps_maskroi_candidates", "vps_track_assign",
     "vps_rpn_finalize", "vps_maskroi_finalize", "vps_select_class", "vps_track_update", "vps_det_split",
-    "vps_mask_removal", "vps_panoptic_fuse", "vps_unify_pan", "vps_unify_pan_ws_bytes", "vps_tube_confusion", "vps_tube_confusion_ws_bytes", "vps_rgb_to_id", "vps_pan2ch_ids",
+    "vps_mask_removal", "vps_panoptic_fuse", "vps_unify_pan", "vps_unify_pan_ws_bytes", "vps_unify_pan_error", "vps_unify_pan_error_offset", "vps_tube_confusion", "vps_tube_confusion_ws_bytes", "vps_rgb_to_id", "vps_pan2ch_ids",
 ]

@@ -7,6 +7,8 @@
 //                          -> a 256-entry look-up table  pan value -> (semantic, instance rank, track id)
 //   3. unify_apply_kernel  out[pixel] = LUT[pan[pixel]]                                  [HBM: 1 map in, 3 channels out]
 // Bit-exact with the reference's numpy (uint8 wrap-around included); no per-region passes, no host round trip.
+#include <stddef.h>
+
 #include "common.cuh"
 
 namespace {
@@ -194,3 +196,15 @@ extern "C" int vps_unify_pan(const void* seg, const void* pan, int label_bytes, 
   VPS_CUDA_LAST("unify_apply");
   return VPS_OK;
 }
+
+// the reference raises IndexError when a panoptic instance id has no cls_ind entry (cityscapes_vps.py:197: cls_ind[id - id_last_stuff - 1]);
+// the decide kernel records that case in the workspace.  Returns the flag of the LAST vps_unify_pan call on `ws` (synchronises `stream`).
+extern "C" int vps_unify_pan_error(const void* ws, void* stream) {
+  int flag = 0;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(&flag, (const char*)ws + offsetof(UnifyWs, error), sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return flag;
+}
+
+// byte offset of the error word inside the workspace (callers that must not synchronise copy it asynchronously)
+extern "C" int64_t vps_unify_pan_error_offset(void) { return (int64_t)offsetof(UnifyWs, error); }

@@ -18,13 +18,16 @@ __global__ void rgb_to_id_kernel(const uint8_t* __restrict__ rgb, int64_t n, uin
     ids[i] = (uint32_t)rgb[3 * i] + 256u * rgb[3 * i + 1] + 65536u * rgb[3 * i + 2];
 }
 
-// segment id of a pixel of the unified 3-channel result (semantic, instance rank, track id): the reference's converter
-// (tools/dataset/cityscapes_vps.py:104-111) keys segments by OFFSET * semantic + track channel and skips VOID (semantic 255);
-// id 0 stays VOID, so the key is shifted by one
-__global__ void pan2ch_ids_kernel(const uint8_t* __restrict__ p2, int64_t n, uint32_t* __restrict__ ids) {
+// segment id of a pixel of the unified 3-channel result (semantic, instance rank, track id).  The reference's converter
+// (tools/dataset/cityscapes_vps.py:104-140) walks the keys OFFSET * semantic + track channel, skips VOID (semantic 255) and
+// makes the segment id the COLOUR panopticapi's IdGenerator returns: one fixed colour per stuff category -- so every key of
+// a stuff category (the native stuff pixels carry their pan value in the track channel, a thing region demoted to stuff
+// carries 0) collapses into ONE segment per frame -- and one colour per (thing category, track) key, kept across frames.
+// Deterministic stand-in for the colours: stuff -> 1000 * semantic + 1, thing -> 1000 * semantic + track + 1, VOID -> 0.
+__global__ void pan2ch_ids_kernel(const uint8_t* __restrict__ p2, int64_t n, uint32_t num_stuff, uint32_t* __restrict__ ids) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t sem = p2[3 * i], trk = p2[3 * i + 2];
-    ids[i] = sem == 255u ? 0u : 1000u * sem + trk + 1u;
+    ids[i] = sem == 255u ? 0u : 1000u * sem + (sem < num_stuff ? 0u : trk) + 1u;
   }
 }
 
@@ -48,10 +51,10 @@ Layout layout(int64_t n, int cap) {
 
 extern "C" int64_t vps_tube_confusion_ws_bytes(int64_t npix) { return npix > 0 ? (int64_t)layout(npix, 0).total : 256; }
 
-extern "C" int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, uint32_t* ids, void* stream) {
+extern "C" int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, int num_stuff, uint32_t* ids, void* stream) {
   if (npix <= 0) return VPS_OK;
   const int blocks = (int)((npix + 255) / 256 > 148 * 16 ? 148 * 16 : (npix + 255) / 256);
-  pan2ch_ids_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pan_2ch, npix, ids);
+  pan2ch_ids_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pan_2ch, npix, (uint32_t)num_stuff, ids);
   VPS_CUDA_LAST("pan2ch_ids");
   return VPS_OK;
 }

@@ -34,6 +34,18 @@ class PanUnifier:
                 self.max_oid += 1
         return out
 
+    def error_word(self):
+        """device view (int32[1]) of the flag `check()` reads: copy it on a side stream to test it without synchronising"""
+        off = int(lib().vps_unify_pan_error_offset())
+        return self._ws[off:off + 4].view(torch.int32)
+
+    def check(self):
+        """Raise what the reference raises (IndexError, cityscapes_vps.py:197) if the last frame held a panoptic instance id
+        without a `cls_ind` entry.  Synchronises the stream: call it where the results are consumed (ClipRunner does, after
+        the download of the frame it yields)."""
+        if self._ws is not None and int(lib().vps_unify_pan_error(ops._ptr(self._ws), ops.stream())) != 0:
+            raise IndexError("get_unified_pan_result: panoptic instance id beyond len(cls_ind)")
+
     @torch.no_grad()
     def __call__(self, seg, pan, cls_ind, obj_id=None, out=None):
         """seg, pan: CUDA label maps [H,W] or [1,H,W] (uint8 or int64); cls_ind, obj_id: per-instance arrays (tensor /

@@ -25,6 +25,7 @@ class ClipRunner:
             from .postproc import PanUnifier
             self.unifier = PanUnifier()
         self._out2 = []
+        self._err = None
         self.dev = torch.device(device) if device is not None else next(det.parameters()).device
         self.copy = torch.cuda.Stream(self.dev)
         self.depth = depth
@@ -115,12 +116,18 @@ class ClipRunner:
                 h2 = self._out2[k2]
                 if h2 is None or h2.shape != p2.shape:
                     h2 = self._out2[k2] = torch.empty(p2.shape, dtype=torch.uint8).pin_memory()
+            herr = None
+            if p2 is not None:
+                if self._err is None:
+                    self._err = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(self.depth + 1)]
+                herr = self._err[i % (self.depth + 1)]
             with torch.cuda.stream(self.copy):
                 self.copy.wait_event(done)
                 hp.copy_(pano, non_blocking=True)
                 hs.copy_(sem, non_blocking=True)
                 if p2 is not None:
                     h2.copy_(p2, non_blocking=True)
+                    herr.copy_(self.unifier.error_word(), non_blocking=True)     # flag of this frame, read without a sync
                 hev.record(self.copy)
             pano.record_stream(self.copy)
             sem.record_stream(self.copy)
@@ -129,9 +136,17 @@ class ClipRunner:
                 r[2]["pan_2ch"] = h2
             if pending is not None:
                 pending[1].synchronize()               # the previous pair's maps are on the host now
+                self._raise_if_flagged(pending[2])
                 yield pending[0]
+
             r[2]["panoptic_outputs"], r[2]["fcn_outputs"] = hp, hs
-            pending = (r, hev)
+            pending = (r, hev, herr)
             i += 1
         pending[1].synchronize()
+        self._raise_if_flagged(pending[2])
         yield pending[0]
+
+    @staticmethod
+    def _raise_if_flagged(herr):
+        if herr is not None and int(herr[0]) != 0:      # what the reference raises (cityscapes_vps.py:197)
+            raise IndexError("get_unified_pan_result: panoptic instance id beyond len(cls_ind)")

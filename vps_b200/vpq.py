@@ -62,13 +62,15 @@ def rgb_to_id(rgb):
 
 def segments_from_pan2ch(pan_2ch, num_stuff=11):
     """Unified 3-channel result (uint8 CUDA [H,W,3], vps_b200.postproc.PanUnifier) -> (id map int32 CUDA [H,W], segments list).
-    The reference's converter (tools/dataset/cityscapes_vps.py:96-131) keys a segment by 1000 * semantic + track channel, skips
-    VOID and gives it a random colour as id; VPQ is invariant to the id values, so the key itself (+1, 0 = VOID) is the id
-    here.  category_id = semantic class, iscrowd = 0, area = pixel count."""
+    The reference's converter (tools/dataset/cityscapes_vps.py:96-140) makes the colour panopticapi's IdGenerator returns the
+    segment id: one fixed colour per stuff category (all its keys merge into one segment per frame), one colour per
+    (thing category, track) key kept across frames.  VPQ is invariant to the id values; the deterministic ids here are
+    1000 * semantic + 1 for stuff (semantic < num_stuff) and 1000 * semantic + track + 1 for things, 0 = VOID.
+    category_id = semantic class, iscrowd = 0, area = pixel count."""
     assert pan_2ch.is_cuda and pan_2ch.dtype == torch.uint8 and pan_2ch.shape[-1] == 3
     pan_2ch = pan_2ch.contiguous()
     ids = torch.empty(pan_2ch.shape[:-1], dtype=torch.int32, device=pan_2ch.device)
-    ops.check(lib().vps_pan2ch_ids(ops._ptr(pan_2ch), C.c_int64(ids.numel()), ops._ptr(ids), ops.stream()), "pan2ch_ids")
+    ops.check(lib().vps_pan2ch_ids(ops._ptr(pan_2ch), C.c_int64(ids.numel()), int(num_stuff), ops._ptr(ids), ops.stream()), "pan2ch_ids")
     pairs, counts = frame_confusion(torch.zeros_like(ids), ids)      # gt = 0: the pair code is the id itself
     segs = []
     for i, a in zip(pairs.tolist(), counts.tolist()):
