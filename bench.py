@@ -272,11 +272,21 @@ def run_gpu_arm(args):
     # of pair i+1 (CUDA graph, second instance) is enqueued before pair i's data-dependent tail, uploads / downloads ride
     # a copy stream.  ONE timed region over all K steps; `value` takes the frames from HBM, `e2e` from pinned host memory.
     from vps_b200.runner import ClipRunner
-    runner = ClipRunner(det, dev)
+    # viper: streaming clips -- the reference frame of frame t is frame t - 1 (cityscapes_vps.py:137-142), so the runner
+    # reuses the previous pair's FPN features as reference features (results bit-identical: tests/test_gpu_e2e.py)
+    runner = ClipRunner(det, dev, streaming=viper)
 
     def region(n, offset, resident):
         src = devp if resident else host
-        pairs = (src[(offset + i) % NPAIR] for i in range(n))
+        if viper:       # a chain: frame k of the clip is src[k % NPAIR][0]; the first frame of a clip references itself
+            def chain():
+                for i in range(n):
+                    k = (offset + i) % CLIP
+                    cur = src[(offset + i) % NPAIR][0]
+                    yield (cur, cur if k == 0 else src[(offset + i - 1) % NPAIR][0])
+            pairs = chain()
+        else:
+            pairs = (src[(offset + i) % NPAIR] for i in range(n))
         metas = (meta(10000 * (1 + rank) + 1 + ((offset + i) % CLIP), H, W) for i in range(n))
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -433,6 +443,9 @@ def run_gpu_arm(args):
                                         "FuseTrack inference, synthetic 2-frame %dx%d pair, " % (H, W)) +
                                        "random-init (synthetic set C) weights, 1 clip stream per GPU",
                            "precision": args.precision,
+                           "ref_feature_cache": ("on: frame t's FPN features are reused as the reference features of frame t+1 "
+                                                 "(one ResNet-50-FPN pass per pair; algorithmic FLOPs still counted on the reference's "
+                                                 "two-pass basis)") if viper else "off (independent pairs)",
                            "parallelism": "clip-sharded replicas x%d, no data-path collective" % world,
                            "l2": "4 rotating input pairs (201 MB of fp32 frames > 126 MB L2) in both timed regions, steps are "
                                  "pipelined so no flush between them; sequential_ms_per_pair flushes 256 MiB between pairs",

@@ -166,6 +166,46 @@ def test_clip_runner_equals_direct_calls(models):
         assert torch.equal(d[2], g[2]) and torch.equal(d[3], g[3])
 
 
+@pytest.mark.parametrize("precision", ["tc32", "bf16"])
+def test_streaming_ref_feature_cache_is_bit_exact(models, precision):
+    """In a clip the reference frame of frame t is frame t - 1 (tools/dataset/cityscapes_vps.py:137-142).
+    ClipRunner(streaming=True) reuses the previous pair's FPN features as the reference features (one ResNet-50-FPN pass
+    per pair instead of two): label maps, class ids and track ids must equal the uncached run bit for bit, with and
+    without the prefetching graph pipeline, across a clip boundary."""
+    from vps_b200.runner import ClipRunner
+    _, prod = models
+    H, W = 128, 256
+    g = torch.Generator().manual_seed(77)
+    imgs = [torch.randn(1, 3, H, W, generator=g) for _ in range(7)]
+    # two clips: frames 0-3 (iid 10001..10004) and 4-6 (iid 20001..20003); the first frame of a clip references itself
+    pairs, metas = [], []
+    for t in range(7):
+        first = t in (0, 4)
+        pairs.append((imgs[t], imgs[t] if first else imgs[t - 1]))
+        metas.append(meta((10001 + t) if t < 4 else (20001 + t - 4), H, W))
+    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in pairs]
+    outs = {}
+    try:
+        prod.precision = precision
+        prod.label_dtype = torch.uint8
+        for mode in ("plain", "stream", "stream_noprefetch"):
+            prod.reset_tracker()
+            res = []
+            runner = ClipRunner(prod, "cuda:0", streaming=mode != "plain")
+            for r in runner.run(pinned, metas, prefetch=mode != "stream_noprefetch"):
+                res.append((r[2]["panoptic_outputs"].clone(), r[2]["fcn_outputs"].clone(),
+                            r[2]["panoptic_det_obj_ids"].cpu().clone(), r[2]["panoptic_cls_inds"].cpu().clone()))
+            outs[mode] = res
+    finally:
+        prod.label_dtype = torch.int64
+        prod.precision = "fp32"
+    for mode in ("stream", "stream_noprefetch"):
+        assert len(outs[mode]) == len(outs["plain"]) == 7
+        for a, b in zip(outs["plain"], outs[mode]):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), mode
+
+
 def test_clip_runner_unified_pan_result(models):
     """ClipRunner(unify=True): the uint8 [H,W,3] image produced on the GPU right after each pair equals the oracle of the
     reference's get_unified_pan_result applied, after the clip, to the collected maps / class ids / track ids."""

@@ -183,7 +183,10 @@ class PanopticFuseTrack(nn.Module):
         return ids
 
     # ------------------------------------------------------------------ static part + CUDA graph
-    def _static_eager(self, img, ref_img, img_shape, taps=None):
+    def _static_eager(self, img, ref_img, img_shape, taps=None, ref_feats=None):
+        """ref_feats: FPN features (tuple of 5 NHWC maps) of the reference frame from an earlier call -- in a clip the
+        reference frame of frame t IS frame t - 1 (tools/dataset/cityscapes_vps.py:137-142), so its features were already
+        computed as `x` of the previous pair; only the current frame then goes through ResNet-50-FPN."""
         dev = img.device
         _, _, H, W = img.shape
         dt = self.act_dtype
@@ -198,9 +201,11 @@ class PanopticFuseTrack(nn.Module):
         # both frames go through ResNet-50-FPN as ONE batch of 2 (the reference runs extract_feat twice,
         # panoptic_fusetrack.py:516-517; frozen BN makes the batched pass identical per image): half the launches, twice
         # the tiles per launch for the small-spatial stages, weights fetched once
-        xr_in = empty_nhwc(2, H, W, 3, dt, dev)
+        nb = 1 if ref_feats is not None else 2
+        xr_in = empty_nhwc(nb, H, W, 3, dt, dev)
         ops.nchw_to_nhwc(img, xr_in[0:1])
-        ops.nchw_to_nhwc(ref_img, xr_in[1:2])
+        if ref_feats is None:
+            ops.nchw_to_nhwc(ref_img, xr_in[1:2])
         feats = self.extract_feat(xr_in)
         br.__exit__(None, None, None)
         if br.side is not None:
@@ -208,7 +213,7 @@ class PanopticFuseTrack(nn.Module):
             flow = self.compute_flow(img, ref_img, 0.25, taps)
             br.join(*feats)
         x = tuple(f[0:1] for f in feats)
-        ref_x = tuple(f[1:2] for f in feats)
+        ref_x = tuple(f[1:2] for f in feats) if ref_feats is None else tuple(ref_feats)
         ops.SCOPE[0] = 'bfp_tcea'
         xf = self.extra_neck(x, ref_x, flow, taps)
         ops.SCOPE[0] = 'upsnet_fpn'
@@ -232,35 +237,44 @@ class PanopticFuseTrack(nn.Module):
                     proposals=proposals_t, rois=rois, nprop=nprop, roi_feats=roi_feats, cls_score=cls_score,
                     bbox_pred=bbox_pred, det_rois=det_rois, cls_idx=cls_idx, cls_prob=cls_prob, kout=kout)
 
-    def _static_part(self, img, ref_img, img_shape, use_graph, taps=None, slot=0):
+    def _static_part(self, img, ref_img, img_shape, use_graph, taps=None, slot=0, ref_feats=None):
         if not use_graph:
-            return self._static_eager(img, ref_img, img_shape, taps)
-        key = (tuple(img.shape), img_shape, self.precision, img.device.index, slot)   # slot: ping-pong graph instance
+            return self._static_eager(img, ref_img, img_shape, taps, ref_feats)
+        cached = ref_feats is not None
+        key = (tuple(img.shape), img_shape, self.precision, img.device.index, slot, cached)   # slot: ping-pong graph instance
         ent = self._graphs.get(key)
         if ent is None:
             # first call for this key runs eagerly (lazy weight packing, function attributes, scratch allocations
             # must happen outside a capture); the second call captures
             self._graphs[key] = "warm"
-            return self._static_eager(img, ref_img, img_shape)
+            return self._static_eager(img, ref_img, img_shape, None, ref_feats)
         if ent == "warm":
             g_img, g_ref = torch.empty_like(img), torch.empty_like(ref_img)
             g_img.copy_(img); g_ref.copy_(ref_img)
+            g_feats = None
+            if cached:          # the graph reads the cached features from its own static buffers
+                g_feats = tuple(torch.empty_like(f) for f in ref_feats)
+                for d_, s_ in zip(g_feats, ref_feats):
+                    d_.copy_(s_)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(graph):
-                outs = self._static_eager(g_img, g_ref, img_shape)
-            ent = self._graphs[key] = (graph, g_img, g_ref, outs, ops.launch_count() - n0)
+                outs = self._static_eager(g_img, g_ref, img_shape, None, g_feats)
+            ent = self._graphs[key] = (graph, g_img, g_ref, outs, ops.launch_count() - n0, g_feats)
             ops.lib().vps_add_launch_count(-ent[4])        # capture itself launched nothing
-        graph, g_img, g_ref, outs, nlaunch = ent
+        graph, g_img, g_ref, outs, nlaunch, g_feats = ent
         g_img.copy_(img, non_blocking=True)
         g_ref.copy_(ref_img, non_blocking=True)
+        if cached:
+            for d_, s_ in zip(g_feats, ref_feats):
+                d_.copy_(s_, non_blocking=True)
         graph.replay()
         ops.lib().vps_add_launch_count(nlaunch)            # kernels of ours re-launched by the replay
         return outs
 
     @torch.no_grad()
-    def prefetch(self, img, img_meta, ref_img=None):
+    def prefetch(self, img, img_meta, ref_img=None, ref_feats=None):
         """Enqueue the static part (flow, backbones, necks, semantic head, RPN, bbox head, MaskROI -- everything that does
         not depend on the tracker) of a FUTURE `simple_test(img, ...)` call on a side stream.  Two graph instances
         ping-pong, so frame i+1's static part overlaps frame i's data-dependent tail and its host round-trips.  The
@@ -284,7 +298,7 @@ class PanopticFuseTrack(nn.Module):
         with torch.cuda.stream(st):
             a = img.contiguous().float()
             b = ref_img.contiguous().float()
-            outs = self._static_part(a, b, tuple(meta['img_shape'][:2]), True, None, slot)
+            outs = self._static_part(a, b, tuple(meta['img_shape'][:2]), True, None, slot, ref_feats)
             ev = torch.cuda.Event()
             ev.record(st)
         img.record_stream(st)
@@ -293,9 +307,11 @@ class PanopticFuseTrack(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
-    def simple_test(self, img, img_meta, proposals=None, rescale=False, ref_img=None, taps=None):
+    def simple_test(self, img, img_meta, proposals=None, rescale=False, ref_img=None, taps=None, ref_feats=None):
         """panoptic_fusetrack.py:502-606.  img / ref_img: NCHW fp32 CUDA tensors [1,3,H,W] (ref_img may be the
-        one-element list the reference's collate produces).  Returns (bbox_results, segm_results, pano_results)."""
+        one-element list the reference's collate produces).  Returns (bbox_results, segm_results, pano_results).
+        ref_feats: optional cached FPN features of ref_img (pano_results['fpn_feats'] of the call that had ref_img as its
+        current frame): skips the reference frame's ResNet-50-FPN pass, results are bit-identical."""
         assert proposals is None
         if isinstance(ref_img, (list, tuple)):
             ref_img = ref_img[0]
@@ -324,7 +340,7 @@ class PanopticFuseTrack(nn.Module):
                         t.record_stream(cur)
         else:
             assert not self._pf_queue, "prefetch() / simple_test() calls out of order"
-            st = self._static_part(img, ref_img, tuple(meta['img_shape'][:2]), use_graph, taps)
+            st = self._static_part(img, ref_img, tuple(meta['img_shape'][:2]), use_graph, taps, 0, ref_feats)
         flow, x, ref_x, xf, fcn_output, fcn_score = st['flow'], st['x'], st['ref_x'], st['xf'], st['fcn_output'], st['fcn_score']
         heads, proposals_t, rois, nprop = st['heads'], st['proposals'], st['rois'], st['nprop']
         roi_feats, cls_score, bbox_pred = st['roi_feats'], st['cls_score'], st['bbox_pred']
@@ -387,6 +403,8 @@ class PanopticFuseTrack(nn.Module):
             # host copies of the two small per-instance arrays (already on the host here): the post-processing that follows
             # the path (vps_b200.postproc.PanUnifier) needs them there
             'host': dict(panoptic_cls_inds=cls_idx_h[keep_h].astype(np.int64), panoptic_det_obj_ids=ids_h[keep_h]),
+            # FPN features of the current frame: a streaming caller hands them back as `ref_feats` of the next pair
+            'fpn_feats': x,
         }
         bbox_results = bbox2result_with_id(det_rois_h[:, 1:], labels_h, ids_h)
         segm_results = [[] for _ in range(self.mask_head.num_classes - 1)]     # :484-485 (`or True`)
