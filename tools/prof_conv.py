@@ -1,5 +1,5 @@
 """Micro-driver for ncu: run ONE representative tensor-core convolution (default: the FPN/TCEA 3x3 256->256
-at 256x512, 154.6 GFLOP) a few times.  Usage: python tools/prof_conv.py [cin cout h w k stride] [--iters N]"""
+at 256x512, 154.6 GFLOP) a few times.  Usage: python tools/prof_conv.py [cin cout h w k stride] [--iters N] [--tc32]"""
 import os
 import sys
 import time
@@ -13,9 +13,13 @@ from vps_b200.layers import Conv  # noqa: E402
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 cin, cout, h, w, k, s = (int(v) for v in args[:6]) if len(args) >= 6 else (256, 256, 256, 512, 3, 1)
 iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 5
+tc32 = "--tc32" in sys.argv                    # fp32 activations through vps_conv2d_tc32 (the parity precision)
+ops.F32_TC[0] = tc32
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-x = torch.randn(1, h, w, cin, generator=g).to(dev).bfloat16()
+x = torch.randn(1, h, w, cin, generator=g).to(dev)
+if not tc32:
+    x = x.bfloat16()
 conv = Conv((torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev), torch.zeros(cout, device=dev),
             stride=s, pad=k // 2, act=ops.ACT_RELU)
 y = conv(x)
