@@ -507,7 +507,9 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(rg.gempty(gb));               // the buffer is free as soon as its values sit in registers
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rg.gempty(gb));   // one arrival per warp (256 per-thread arrivals on one mbarrier serialise): the
+                                                     // buffer is free as soon as its values sit in registers
         if (has_b) {
           if (g == 0) {
 #pragma unroll
@@ -538,7 +540,8 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
         tmem_ld_wait();
       }
       tc_fence_before();
-      mbar_arrive(rg.cempty(cb));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.cempty(cb));
       if (has_b) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum[1][j] = __fmaf_rn(__uint_as_float(r[j]), T32_LO_INV, sum[1][j]);
@@ -594,7 +597,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;      // sempty, pfull: every converter thread
       if ((i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) || (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES)) count = 2;   // pempty, bempty: both issuers
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
-        count = 32 * T32_EPI_WARPS;                                               // gempty, cempty: every promotion thread
+        count = T32_EPI_WARPS;                                                    // gempty, cempty: one arrival per promotion warp
       mbar_init(rg.bar_base + 8u * i, count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -666,7 +669,7 @@ dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParam
       if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;
       if ((i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) || (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES)) count = 2;
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
-        count = 32 * T32_EPI_WARPS;
+        count = T32_EPI_WARPS;
       mbar_init(rg.bar_base + 8u * i, count);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
