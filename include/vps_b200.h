@@ -353,6 +353,13 @@ int vps_rgb_to_id(const uint8_t* rgb, int64_t npix, uint32_t* ids, void* stream)
  * (id 1000 * semantic + track + 1), VOID (semantic 255) -> 0 */
 int vps_pan2ch_ids(const uint8_t* pan_2ch, int64_t npix, int num_stuff, uint32_t* ids, void* stream);
 
+/* ---- input stage -----------------------------------------------------------------------------------------
+ * Normalize (mmcv.imnormalize: float32, BGR->RGB, (x - mean) / std; transforms.py:295-318) + Pad(size_divisor) (zero pad bottom /
+ * right, :238-270) + ImageToTensor (HWC -> CHW, formating.py:46-68) of one uint8 HWC BGR frame in one pass: out is fp32 NCHW
+ * [1,3,hp,wp].  mean3 / std3 are HOST arrays in output-channel order (RGB when to_rgb).  Bit-identical to the numpy arithmetic. */
+int vps_preprocess_u8(const uint8_t* bgr_hwc, int h, int w, const float* mean3, const float* std3, int to_rgb,
+                      float* out_nchw, int hp, int wp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
