@@ -185,6 +185,11 @@ int vps_resize_nearest(const vps_tensor* src, const vps_tensor* out, float mul, 
 /* space-to-depth, block 2: y[n,Y,X,(dy*2+dx)*C+c] = x[n,2Y+dy,2X+dx,c].  Lets the 7x7 stride-2 stem convolutions
  * (resnet.py:436-451, FlowNetC.py:20 / FlowNetS.py:20 conv1) run as 4x4 stride-1 implicit GEMMs on the tensor cores. */
 int vps_space_to_depth2(const vps_tensor* x, const vps_tensor* y, void* stream);
+/* second half of a 3x3 / stride 1 / pad 1 convolution with <= 3 output channels (FlowNet2 predict_flow*, submodules.py:27-28)
+ * whose first half ran as a 1x1 convolution with the taps on the output-channel axis (z[p][t*cout+co], t = 3*r+s):
+ * out[n,y,x,co] = act(bias[co] + sum_t z[n, y+r-1, x+s-1, t*cout+co]) * out_scale, zero outside the map.  fp32 tensors. */
+int vps_tap_gather3x3(const vps_tensor* z, const vps_tensor* out, const float* bias, int act, float slope, float out_scale,
+                      void* stream);
 /* max / avg pool (resnet.py:451, tcea_modules.py:27-28; avg = count_include_pad) */
 int vps_pool2d(const vps_tensor* src, const vps_tensor* out, int k, int s, int p, int is_avg, void* stream);
 /* GroupNorm(groups, eps) + optional ReLU (upsnetFPN.py:42-51) */

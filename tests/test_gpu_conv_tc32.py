@@ -143,3 +143,30 @@ def test_linear_tc32(cuda, tc32):
     torch.cuda.synchronize()
     err = (y.cpu().double() - ref).abs().max().item()
     assert err <= TOL * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("cin,h,w,cout", [(194, 24, 40, 2), (1026, 8, 16, 2), (16, 33, 47, 2), (64, 16, 16, 3)])
+def test_thin_3x3_as_tap_major_1x1(cuda, tc32, cin, h, w, cout):
+    """predict_flow layers (3x3, cout <= 3): 1x1 tensor-core convolution over tap-major output channels + vps_tap_gather3x3,
+    written into a channel slice of a wider concat buffer like the FlowNet decoders do"""
+    ops = tc32
+    from vps_b200.layers import Conv, empty_nhwc
+    g = torch.Generator().manual_seed(7 + cin)
+    x = torch.randn(1, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x.double(), wt.double(), b.double(), padding=1), 0.1) * 0.5
+    layer = Conv(wt.to(cuda), b.to(cuda), stride=1, pad=1, act=ops.ACT_LRELU)
+    assert layer.pk_tap is not None
+    xd = empty_nhwc(1, h, w, cin, torch.float32, cuda)
+    xd.copy_(x.permute(0, 2, 3, 1).to(cuda))
+    cat = torch.full((1, h, w, 24), float("nan"), dtype=torch.float32, device=cuda)
+    layer(xd, cat[..., 5:5 + cout], out_scale=0.5)   # first call packs the weights
+    n0 = ops.launch_count()
+    layer(xd, cat[..., 5:5 + cout], out_scale=0.5)
+    assert ops.launch_count() - n0 == 2              # the 1x1 tensor-core GEMM + the gather
+    torch.cuda.synchronize()
+    got = cat[..., 5:5 + cout].cpu().permute(0, 3, 1, 2).double()
+    assert torch.isnan(cat[..., :5]).all() and torch.isnan(cat[..., 5 + cout:]).all()
+    err = (got - ref).abs().max().item()
+    assert err <= TOL * max(1.0, ref.abs().max().item()), err

@@ -50,6 +50,7 @@ constexpr int T32_MAX_MAIN = 8;
 constexpr int T32_STAGE_SLOTS = 2;          // fp32 staging boxes (TMA -> converters)
 constexpr int T32_PLANES = 2;               // operand planes: fp16(v), fp16(2^11 (v - fp16(v)))
 constexpr float T32_LO_SCALE = 2048.f, T32_LO_INV = 1.f / 2048.f;
+constexpr uint32_t T32_SCRATCH_BYTES = 8u * 4096u;     // TMA-store epilogue: one [32 px][32 ch] fp32 box per promotion warp
 
 __device__ unsigned int g_tc32_overflow = 0;     // activations / weights that exceeded the fp16 range of the main product
 
@@ -70,6 +71,15 @@ struct Dcn32Params {
   int x_cs, off_cs, H, W;
 };
 constexpr int DCN32_SETUP_BYTES = 9 * BLOCK_M * 32;      // per (tap, pixel): 4 bilinear weights + 4 element offsets
+// the fused DCN kernel is bound by its sampling warps (CUDA-core issue + L1 latency: 5 warps needed ~3900 clocks per K step
+// against 384 clocks of MMA time), so it runs 6 warpgroups: warps 0-2 TMA / MMA issuers, warps 3-7 and 16-23 = 13 sampling
+// warps, warps 8-15 promotion + epilogue
+#ifndef VPS_DCN32_THREADS
+#define VPS_DCN32_THREADS 768
+#endif
+constexpr int DCN32_THREADS = VPS_DCN32_THREADS;
+constexpr int DCN32_GATHER_WARPS = DCN32_THREADS == 768 ? 13 : 5;
+constexpr int DCN32_UNITS_PER_STEP = 16;                 // 8-row x 32-channel units of one K step
 
 struct Ring32 {
   uint32_t s_base, s_bytes;      // staging ring
@@ -241,14 +251,18 @@ __device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Ext
 // fp16 planes straight into the operand ring -- the 9x column matrix (1.2 GB per P2 layer in fp32) never exists.  K steps run
 // chunk-major / tap-minor: the nine taps of a 32-channel chunk re-read the same few KB of input from L1.
 __device__ __forceinline__ void dcn_gather32(const ConvTcParams& p, const Tc32Extra& e, const Dcn32Params& d, const Ring32& rg,
-                                             uint32_t setup_base, int gtid) {
-  constexpr int NT = 32 * T32_CONV_WARPS;
+                                             uint32_t setup_base, uint32_t ctr_addr, int gtid) {
+  constexpr int NT = 32 * DCN32_GATHER_WARPS;
   const int H = d.H, W = d.W;
-  int as = 0;
-  uint32_t aphase = 0;
-  const int j = gtid & 3;                    // 8-channel group of the 32-channel chunk
+  const int lane = gtid & 31;
+  const int j = lane & 3;                    // 8-channel group of the 32-channel chunk
+  const int steps_per_tile = p.cin_chunks * 9;
+  const uint32_t units_per_tile = (uint32_t)steps_per_tile * 16u;      // a unit = 8 rows (pixels) x 32 channels of one K step
+  const uint32_t a_stages = (uint32_t)p.a_stages;
+  uint32_t step_base = 0;                    // K steps of the tiles this CTA has finished
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = tile_coord(p, tile);
+    if (gtid == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctr_addr), "r"(0u) : "memory");
     // ---- sampling set-up of all (tap, pixel) pairs of this tile
     for (int item = gtid; item < 9 * BLOCK_M; item += NT) {
       const int k = item >> 7, r = item & (BLOCK_M - 1);
@@ -278,51 +292,65 @@ __device__ __forceinline__ void dcn_gather32(const ConvTcParams& p, const Tc32Ex
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16u), "r"(offs[0]), "r"(offs[1]), "r"(offs[2]), "r"(offs[3]) : "memory");
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+    // ---- units are claimed dynamically (any number of gather warps stays balanced; a warp may run ahead into the next
+    //      K step's ring slot): unit u = (K step u / 16, rows 8 * (u % 16) ..), K steps chunk-major / tap-minor
+    while (true) {
+      uint32_t u = 0;
+      if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(u) : "r"(ctr_addr) : "memory");
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= units_per_tile) break;
+      const uint32_t step = u >> 4, part = u & 15u;
+      const uint32_t cc = step / 9u, k = step - cc * 9u;
+      const uint32_t sg = step_base + step;             // K step counted over all tiles of this CTA -> ring slot and its use count
+      const uint32_t use = sg / a_stages, as = sg - use * a_stages;
+      mbar_wait(rg.pempty((int)as), (use & 1u) ^ 1u);
+      const uint32_t dst = rg.a_base + as * rg.a_bytes;
+      const int r = (int)(part * 8u) + (lane >> 2);
       const float* xc = d.x + cc * T32_KC + j * 8;
-      for (int k = 0; k < 9; ++k) {
-        mbar_wait(rg.pempty(as), aphase ^ 1);
-        const uint32_t dst = rg.a_base + as * rg.a_bytes;
-        for (int r = gtid >> 2; r < BLOCK_M; r += NT / 4) {
-          const uint32_t sa = setup_base + (uint32_t)(k * BLOCK_M + r) * 32u;
-          float wq[4];
-          int oq[4];
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wq[0]), "=f"(wq[1]), "=f"(wq[2]), "=f"(wq[3]) : "r"(sa));
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(oq[0]), "=r"(oq[1]), "=r"(oq[2]), "=r"(oq[3]) : "r"(sa + 16u));
-          float acc[8];
+      {
+        const uint32_t sa = setup_base + (uint32_t)(k * BLOCK_M + r) * 32u;
+        float wq[4];
+        int oq[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wq[0]), "=f"(wq[1]), "=f"(wq[2]), "=f"(wq[3]) : "r"(sa));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(oq[0]), "=r"(oq[1]), "=r"(oq[2]), "=r"(oq[3]) : "r"(sa + 16u));
+        float acc[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-          // the reference accumulates w1*v1 + w2*v2 + w3*v3 + w4*v4 left to right (dmcn_im2col_bilinear); same order here
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        // the reference accumulates w1*v1 + w2*v2 + w3*v3 + w4*v4 left to right (dmcn_im2col_bilinear); same order here
+        float4 v0[4], v1[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {           // corners outside the image carry weight 0 (branch-free: finite inputs)
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(xc + oq[c]));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(xc + oq[c]) + 1);
-            acc[0] += wq[c] * v0.x; acc[1] += wq[c] * v0.y; acc[2] += wq[c] * v0.z; acc[3] += wq[c] * v0.w;
-            acc[4] += wq[c] * v1.x; acc[5] += wq[c] * v1.y; acc[6] += wq[c] * v1.z; acc[7] += wq[c] * v1.w;
-          }
-          unsigned short hb[8], lb[8];
-          bool over = false, dummy = false;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float lo = acc[q] - to_f16_sat(acc[q], hb[q], over);
-            to_f16_sat(lo * T32_LO_SCALE, lb[q], dummy);
-          }
-          if (over) atomicAdd(&g_tc32_overflow, 1u);
-          const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
-          const uint32_t pm = dst + off, pl = pm + (uint32_t)e.plane_bytes;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"((uint32_t)hb[0] | ((uint32_t)hb[1] << 16)),
-                       "r"((uint32_t)hb[2] | ((uint32_t)hb[3] << 16)), "r"((uint32_t)hb[4] | ((uint32_t)hb[5] << 16)),
-                       "r"((uint32_t)hb[6] | ((uint32_t)hb[7] << 16)) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"((uint32_t)lb[0] | ((uint32_t)lb[1] << 16)),
-                       "r"((uint32_t)lb[2] | ((uint32_t)lb[3] << 16)), "r"((uint32_t)lb[4] | ((uint32_t)lb[5] << 16)),
-                       "r"((uint32_t)lb[6] | ((uint32_t)lb[7] << 16)) : "memory");
+        for (int c = 0; c < 4; ++c) {           // corners outside the image carry weight 0 (branch-free: finite inputs)
+          v0[c] = __ldg(reinterpret_cast<const float4*>(xc + oq[c]));
+          v1[c] = __ldg(reinterpret_cast<const float4*>(xc + oq[c]) + 1);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(rg.pfull(as));
-        if (++as == p.a_stages) { as = 0; aphase ^= 1; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[0] += wq[c] * v0[c].x; acc[1] += wq[c] * v0[c].y; acc[2] += wq[c] * v0[c].z; acc[3] += wq[c] * v0[c].w;
+          acc[4] += wq[c] * v1[c].x; acc[5] += wq[c] * v1[c].y; acc[6] += wq[c] * v1[c].z; acc[7] += wq[c] * v1[c].w;
+        }
+        unsigned short hb[8], lb[8];
+        bool over = false, dummy = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float lo = acc[q] - to_f16_sat(acc[q], hb[q], over);
+          to_f16_sat(lo * T32_LO_SCALE, lb[q], dummy);
+        }
+        if (over) atomicAdd(&g_tc32_overflow, 1u);
+        const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
+        const uint32_t pm = dst + off, pl = pm + (uint32_t)e.plane_bytes;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"((uint32_t)hb[0] | ((uint32_t)hb[1] << 16)),
+                     "r"((uint32_t)hb[2] | ((uint32_t)hb[3] << 16)), "r"((uint32_t)hb[4] | ((uint32_t)hb[5] << 16)),
+                     "r"((uint32_t)hb[6] | ((uint32_t)hb[7] << 16)) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"((uint32_t)lb[0] | ((uint32_t)lb[1] << 16)),
+                     "r"((uint32_t)lb[2] | ((uint32_t)lb[3] << 16)), "r"((uint32_t)lb[4] | ((uint32_t)lb[5] << 16)),
+                     "r"((uint32_t)lb[6] | ((uint32_t)lb[7] << 16)) : "memory");
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.pfull((int)as));                   // 16 warp-units complete a K step's operand planes
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");      // the set-up table is rewritten for the next tile
+    step_base += (uint32_t)steps_per_tile;
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");      // the set-up table and the unit counter are rewritten for the next tile
   }
 }
 
@@ -459,12 +487,90 @@ __device__ __forceinline__ void mma32_dispatch(const ConvTcParams& p, const Tc32
   }
 }
 
+// ---------------------------------------------------------------- TMA-store epilogue of one 32-channel chunk
+// The promotion leaves a lane with ONE pixel and 32 channels.  Stores from that layout cost either 32 partial-line write
+// requests per instruction (256-bit stores: 4.0k clocks per 128 x 128 tile in tools/mb/mb_store.cu, and the bias / activation /
+// address code in front of them made the whole epilogue 13k clocks -- ncu: the promotion warps are issue-latency bound, ~2000
+// dependent instructions per tile) or a shuffle transpose that needs even more instructions.  Instead every promotion warp owns
+// a 4 KB SWIZZLE_128B scratch: a lane writes its 32 finished values as eight conflict-free 16-byte stores, and one elected lane
+// hands the [32 pixels][32 channels] box to the TMA, which writes full lines, clips pixels / channels outside the output
+// tensor and runs asynchronously to the next chunk's arithmetic.  A warp's 32 pixels are rows q*32 .. q*32+31 of the tile =
+// a bw x bh pixel box (bw = min(tw, 32)).
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the calling lane's earlier bulk stores have finished READING shared memory (the scratch may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// v: the lane's 32 promoted sums for channels n0 .. n0+31 of its pixel `pix` (valid = inside the output); all 32 lanes call
+// PLAIN: no bias / residual / activation / scale (the DCN kernel)
+template <int ACT, bool PLAIN>
+__device__ __forceinline__ void epi_chunk_tma(const ConvTcParams& p, const CUtensorMap* tmY, uint32_t scratch, float (&v)[32], int lane,
+                                              int64_t pix, bool valid, int n0, int nlim, int x0, int y0, int img) {
+  const int nv = min(32, nlim - n0);
+  if (!PLAIN) {
+  if (p.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);   // n0 % 32 == 0, bias 16-byte aligned (host check)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (4 * j + 3 < nv) {
+        const float4 b = __ldg(bp + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (4 * j + c < nv) v[4 * j + c] += __ldg(p.bias + n0 + 4 * j + c);
+      }
+    }
+  }
+  // fp32 residual with 16-byte aligned rows (host check); channels past nlim are never stored (the TMA clips them)
+  const float* rq = p.res ? (const float*)p.res + pix * p.res_cs + n0 : nullptr;
+  auto add_res = [&]() {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (valid && 4 * j < nv) {
+        const float4 f = *reinterpret_cast<const float4*>(rq + 4 * j);
+        v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+      }
+    }
+  };
+  if (rq && !p.res_after_act) add_res();
+  const float scale = p.out_scale;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float t = v[j];
+    const int act = ACT < 0 ? p.act : ACT;
+    if (act == VPS_ACT_RELU) t = fmaxf(t, 0.f);
+    else if (act == VPS_ACT_LRELU) t = t > 0.f ? t : t * p.slope;
+    else if (act == VPS_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+    v[j] = t * scale;
+  }
+  if (rq && p.res_after_act) add_res();
+  }
+  // the previous box of this warp must have left the scratch
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  const uint32_t row = scratch + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((((uint32_t)j) ^ sw) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) tma_store_4d(tmY, scratch, n0, x0, y0, img);
+}
+
 // ---------------------------------------------------------------- warps 8..15: promotion (TMEM groups -> register sums) + epilogue
 // warp -> TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter take alternate 32-column
 // chunks, so a thread owns one output pixel and up to 2 x 32 channels of running sums.
-template <int ACT, bool STATS>
+template <int ACT, bool STATS, bool PLAIN = false>
 __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base,
-                                                 int warp, int lane) {
+                                                 int warp, int lane, const CUtensorMap* tmY, uint32_t scratch_base) {
   const int q = warp & 3, half = (warp - 8) >> 2;
   const int row = q * 32 + lane;
   const int ty_in = row / p.tw, tx_in = row - ty_in * p.tw;
@@ -566,7 +672,13 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int c0 = (half + 2 * k) * 32;
-      if (c0 < bn && valid && nbase + c0 < nlim) {
+      if (c0 >= bn || nbase + c0 >= nlim) continue;
+      if (p.epi_t == 2) {                           // warp-uniform: TMA store through this warp's scratch (clips partial chunks)
+        const int row_w = row & ~31;                // the warp's first tile row -> top-left pixel of its bw x bh box
+        const int ty_w = row_w / p.tw, tx_w = row_w - ty_w * p.tw;
+        epi_chunk_tma<ACT, PLAIN>(p, tmY, scratch_base + (uint32_t)(warp - 8) * 4096u, sum[k], lane, pix, valid, nbase + c0, nlim,
+                           tx * p.tw + tx_w, ty * p.th + ty_w, img);
+      } else if (!PLAIN && valid) {                 // (the DCN kernel only has the TMA epilogue: host check)
         uint32_t r[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(sum[k][j]);
@@ -575,20 +687,22 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
     }
     if (st) t_store += clock64() - t1;
   }
+  if (p.epi_t == 2 && lane == 0) tma_store_wait_all();      // the last boxes are in global memory before the CTA exits
   if (st && warp == 8 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = w_g; p.stats[blockIdx.x * 8 + 6] = t_store; }
 }
 
 // ---------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(T32_THREADS, 1)
-conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p,
-                       const Tc32Extra e) {
+conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmY, const ConvTcParams p, const Tc32Extra e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Ring32 rg;
   rg.s_base = smem_base; rg.s_bytes = (uint32_t)e.stage_bytes;
   rg.a_base = rg.s_base + T32_STAGE_SLOTS * rg.s_bytes; rg.a_bytes = (uint32_t)T32_PLANES * (uint32_t)e.plane_bytes;
   rg.b_base = rg.a_base + (uint32_t)p.a_stages * rg.a_bytes; rg.b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
-  rg.bar_base = rg.b_base + (uint32_t)p.b_stages * rg.b_bytes;
+  const uint32_t scratch_base = rg.b_base + (uint32_t)p.b_stages * rg.b_bytes;      // 8 x 4 KB epilogue scratch (epi_t == 2)
+  rg.bar_base = scratch_base + (p.epi_t == 2 ? T32_SCRATCH_BYTES : 0u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 2) {
@@ -605,6 +719,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.epi_t == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync()), "r"(0u) : "memory");
   }
   if (warp == 1) {
@@ -631,13 +746,13 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T32_REGS_HIGH));
     if (p.stats) {     // debugging aid (VPS_CONV_STATS=1): clocks of the generic path only
-      promote_epilogue<-1, true>(p, e, rg, tmem_base, warp, lane);
+      promote_epilogue<-1, true>(p, e, rg, tmem_base, warp, lane, &tmY, scratch_base);
     } else {
       switch (p.act) {
-        case VPS_ACT_RELU: promote_epilogue<VPS_ACT_RELU, false>(p, e, rg, tmem_base, warp, lane); break;
-        case VPS_ACT_LRELU: promote_epilogue<VPS_ACT_LRELU, false>(p, e, rg, tmem_base, warp, lane); break;
-        case VPS_ACT_SIGMOID: promote_epilogue<VPS_ACT_SIGMOID, false>(p, e, rg, tmem_base, warp, lane); break;
-        default: promote_epilogue<VPS_ACT_NONE, false>(p, e, rg, tmem_base, warp, lane); break;
+        case VPS_ACT_RELU: promote_epilogue<VPS_ACT_RELU, false>(p, e, rg, tmem_base, warp, lane, &tmY, scratch_base); break;
+        case VPS_ACT_LRELU: promote_epilogue<VPS_ACT_LRELU, false>(p, e, rg, tmem_base, warp, lane, &tmY, scratch_base); break;
+        case VPS_ACT_SIGMOID: promote_epilogue<VPS_ACT_SIGMOID, false>(p, e, rg, tmem_base, warp, lane, &tmY, scratch_base); break;
+        default: promote_epilogue<VPS_ACT_NONE, false>(p, e, rg, tmem_base, warp, lane, &tmY, scratch_base); break;
       }
     }
   }
@@ -651,9 +766,16 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------- fused DCNv1 kernel (same pipeline, sampling warps feed the ring)
-constexpr int DCN32_REGS_LOW = 80, DCN32_REGS_HIGH = 176;      // 256 * 80 + 256 * 176 = 65536
-__global__ void __launch_bounds__(T32_THREADS, 1)
-dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParams p, const Tc32Extra e, const Dcn32Params d) {
+#ifndef VPS_DCN32_LOW        // setmaxnreg redistributes the CTA's OWN allocation (768 threads x 80 registers = 61440): a split
+#define VPS_DCN32_LOW 48     // that needs more leaves promotion warps spinning in setmaxnreg.inc forever (measured: deadlock)
+#define VPS_DCN32_HIGH 144   // 512 * 48 + 256 * 144 = 61440
+#endif
+constexpr int DCN32_REGS_LOW = DCN32_THREADS == 768 ? VPS_DCN32_LOW : 80;
+constexpr int DCN32_REGS_HIGH = DCN32_THREADS == 768 ? VPS_DCN32_HIGH : 176;     // 512 threads: 256 * 80 + 256 * 176 = 65536
+static_assert(DCN32_THREADS != 768 || 512 * DCN32_REGS_LOW + 256 * DCN32_REGS_HIGH <= 768 * 80, "setmaxnreg pool = launch allocation");
+__global__ void __launch_bounds__(DCN32_THREADS, 1)
+dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const ConvTcParams p,
+                      const Tc32Extra e, const Dcn32Params d) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Ring32 rg;
@@ -661,12 +783,14 @@ dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParam
   rg.a_base = smem_base; rg.a_bytes = (uint32_t)T32_PLANES * (uint32_t)e.plane_bytes;
   rg.b_base = rg.a_base + (uint32_t)p.a_stages * rg.a_bytes; rg.b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
   const uint32_t setup_base = rg.b_base + (uint32_t)p.b_stages * rg.b_bytes;
-  rg.bar_base = setup_base + DCN32_SETUP_BYTES;
+  const uint32_t scratch_base = setup_base + DCN32_SETUP_BYTES;
+  rg.bar_base = scratch_base + (p.epi_t == 2 ? T32_SCRATCH_BYTES : 0u);
+  const uint32_t ctr_addr = rg.issue_sync() + 8u;           // unit counter of the sampling warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 2) {
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
-      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;
+      if (i >= 2 * MAX_STAGES && i < 3 * MAX_STAGES) count = DCN32_UNITS_PER_STEP;      // pfull: one arrival per warp-unit
       if ((i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) || (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES)) count = 2;
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
         count = T32_EPI_WARPS;
@@ -690,15 +814,15 @@ dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const ConvTcParam
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(rg.tmem_slot()) : "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (warp < 8) {
+  if (warp < 8 || warp >= 16) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCN32_REGS_LOW));
     if (warp == 0) producer32(p, e, rg, &tmB, &tmB);
     else if (warp == 1) mma32<0, false, false>(p, e, rg, tmem_base);
     else if (warp == 2) mma32<1, false, false>(p, e, rg, tmem_base);
-    else dcn_gather32(p, e, d, rg, setup_base, (int)threadIdx.x - 96);
+    else dcn_gather32(p, e, d, rg, setup_base, ctr_addr, warp < 8 ? (int)threadIdx.x - 96 : (int)threadIdx.x - 512 + 160);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCN32_REGS_HIGH));
-    promote_epilogue<VPS_ACT_NONE, false>(p, e, rg, tmem_base, warp, lane);
+    promote_epilogue<VPS_ACT_NONE, false, true>(p, e, rg, tmem_base, warp, lane, &tmY, scratch_base);
   }
   tc_fence_before();
   __syncthreads();
@@ -846,7 +970,21 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   e.nk_last = (rem + 15) / 16;
   const int ntaps = a->kh * a->kw;
   p.a_stages = halo ? 2 : 3;
-  const int smem_budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64;
+  // epilogue: 2 = TMA store through per-warp scratch boxes (fp32 output that maps 1:1 onto the output tensor, 16-byte aligned
+  // rows; a residual must be fp32 with aligned rows), 1 = shuffle-transposed 128-bit stores, 0 = per-lane stores (bf16 output,
+  // interleaved transposed-convolution phases, mis-aligned slices)
+  {
+    static int epi_env = -1;
+    if (epi_env < 0) { const char* ev = getenv("VPS_TC32_EPI"); epi_env = ev ? atoi(ev) : 2; }
+    const bool y_ok = a->y.dtype == VPS_F32 && (((uintptr_t)a->y.ptr & 15) == 0) && (a->y.cs % 4 == 0);
+    const bool r_ok = !a->res.ptr || (a->res.dtype == VPS_F32 && (((uintptr_t)a->res.ptr & 15) == 0) && (a->res.cs % 4 == 0));
+    const bool plain = nprob == 1 && a->oy_mul == 1 && a->ox_mul == 1 && a->oy_off == 0 && a->ox_off == 0 && a->y.h == a->oh &&
+                       a->y.w == a->ow && a->y.c == a->cout;
+    p.epi_t = (y_ok && r_ok) ? 1 : 0;
+    if (p.epi_t && plain && epi_env >= 2) p.epi_t = 2;
+    if (epi_env == 0) p.epi_t = 0;
+  }
+  const int smem_budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64 - (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
   const int a_side = T32_STAGE_SLOTS * e.stage_bytes + p.a_stages * p.a_stage_bytes;
   // N tile: divisor of cout_pad (multiple of 16, <= 128) minimising waves * (steps * step clocks + epilogue); a step is
   // 6 MMAs = 3*bn clocks at the MMA floor, ~300 clocks of issue / barrier latency, or its weight bytes at the L2 rate
@@ -857,6 +995,8 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
     for (int bn = 16; bn <= T32_MAX_N && bn <= cout_pad; bn += 16) {
       if (cout_pad % bn) continue;
       if (a_side + 2 * bn * 64 * T32_PLANES > smem_budget) continue;
+      // TMA-store epilogue: boxes are 32 channels wide and only clipped at the END of the tensor's channel axis
+      if (p.epi_t == 2 && (bn % 32) && bn != cout_pad) continue;
       const int64_t tiles = m_tiles * (cout_pad / bn);
       const double waves = (double)((tiles + g_num_sms32 - 1) / g_num_sms32);
       const double step = fmax(fmax(300.0, 3.0 * bn), (double)(bn * 64 * T32_PLANES) / 56.0);
@@ -930,7 +1070,21 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc32: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
-  const int smem = a_side + p.b_stages * T32_PLANES * e.b_plane_bytes + 1024 + T32_BAR_BYTES;
+  CUtensorMap tmY = tmB;      // unused unless epi_t == 2
+  if (p.epi_t == 2) {
+    const int bw = p.tw < 32 ? p.tw : 32, bh = 32 / bw;
+    cuuint64_t dims[4] = {(cuuint64_t)a->y.c, (cuuint64_t)a->y.w, (cuuint64_t)a->y.h, (cuuint64_t)a->y.n};
+    cuuint64_t strides[3] = {(cuuint64_t)a->y.cs * 4, (cuuint64_t)a->y.w * a->y.cs * 4, (cuuint64_t)a->y.h * a->y.w * a->y.cs * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->y.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vps::set_error("conv2d_tc32: encode Y failed (%d) dims %d,%d,%d,%d cs %d", (int)r, a->y.c, a->y.w, a->y.h, a->y.n, a->y.cs);
+      return VPS_E_CUDA;
+    }
+  }
+  const int smem = a_side + p.b_stages * T32_PLANES * e.b_plane_bytes + 1024 + T32_BAR_BYTES + (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
   static bool smem_set = false;
   if (!smem_set) {
     if (cudaFuncSetAttribute(conv_igemm_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -954,7 +1108,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_tc32_kernel, tmA, tmB, p, e);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_igemm_tc32_kernel, tmA, tmB, tmY, p, e);
   if (le != cudaSuccess) { vps::set_error("conv2d_tc32: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
   VPS_CUDA_LAST("conv_igemm_tc32_kernel");
   if (stats_env) {
@@ -1011,6 +1165,7 @@ extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offse
   p.tiles_x = vps::cdiv(x->w, p.tw); p.tiles_y = vps::cdiv(x->h, p.th);
   int block_n = cout_pad;
   while (block_n > T32_MAX_N || cout_pad % block_n) block_n -= 16;
+  VPS_CHECK_ARG(block_n % 32 == 0 || block_n == cout_pad, "deform_conv_tc32: cout %d has no N tile the TMA epilogue can store", cout);
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
   p.kh = p.kw = 3; p.sh = p.sw = 1; p.halo = 0; p.halo_w = 0;
   p.cin_chunks = x->c / T32_KC;
@@ -1021,11 +1176,29 @@ extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offse
   e.nmain = block_n <= 64 ? 6 : 3;
   e.ncorr = block_n <= 64 ? 2 : 1;
   p.a_box_bytes = 0; p.a_stage_bytes = T32_PLANES * e.plane_bytes;
-  p.a_stages = 3;
+  // Shared memory is kept SMALL on purpose (<= 132 KB -> the 132 KB carve-out, ~120 KB of L1 left): the sampling warps read
+  // 4 x 128 B per (tap, pixel, 32-channel chunk) through L1, and the nine taps of a chunk re-read the same ~60 KB footprint of
+  // the tile.  With the rings sized like the convolution kernel's (212 KB) only ~28 KB of L1 remained, every tap missed, and the
+  // kernel moved ~9.7 GB through L2 per 256->256 layer at 256x512 (1.8-2.1 ms, L2-bandwidth bound whatever the number of
+  // sampling warps).
   {
-    const int budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64 - DCN32_SETUP_BYTES - p.a_stages * p.a_stage_bytes;
+    static int epi_env = -1;
+    if (epi_env < 0) { const char* ev = getenv("VPS_TC32_EPI"); epi_env = ev ? atoi(ev) : 2; }
+    (void)epi_env;
+    VPS_CHECK_ARG(y->dtype == VPS_F32 && (((uintptr_t)y->ptr & 15) == 0) && (y->cs % 4 == 0),
+                  "deform_conv_tc32: y must be fp32 with 16-byte aligned pixel rows (cs=%d)", y->cs);
+    p.epi_t = 2;
+  }
+  static int dcn_a_env = -1, dcn_b_env = -1;
+  if (dcn_a_env < 0) { const char* ev = getenv("VPS_DCN32_A_STAGES"); dcn_a_env = ev ? atoi(ev) : 2; }
+  if (dcn_b_env < 0) { const char* ev = getenv("VPS_DCN32_B_STAGES"); dcn_b_env = ev ? atoi(ev) : 3; }
+  p.a_stages = dcn_a_env < 2 ? 2 : (dcn_a_env > 3 ? 3 : dcn_a_env);
+  {
+    const int budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64 - DCN32_SETUP_BYTES - p.a_stages * p.a_stage_bytes -
+                       (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
     int bst = budget / (T32_PLANES * e.b_plane_bytes);
     p.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
+    if (p.b_stages > dcn_b_env && dcn_b_env >= 2) p.b_stages = dcn_b_env;
     VPS_CHECK_ARG(p.b_stages >= 2, "deform_conv_tc32: ring does not fit");
   }
   static int group_env = -1;
@@ -1054,24 +1227,39 @@ extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offse
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("deform_conv_tc32: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
-  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * T32_PLANES * e.b_plane_bytes + DCN32_SETUP_BYTES + 1024 + T32_BAR_BYTES;
+  CUtensorMap tmY = tmB;
+  if (p.epi_t == 2) {
+    const int bw = p.tw < 32 ? p.tw : 32, bh = 32 / bw;
+    cuuint64_t dims[4] = {(cuuint64_t)y->c, (cuuint64_t)y->w, (cuuint64_t)y->h, (cuuint64_t)y->n};
+    cuuint64_t strides[3] = {(cuuint64_t)y->cs * 4, (cuuint64_t)y->w * y->cs * 4, (cuuint64_t)y->h * y->w * y->cs * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vps::set_error("deform_conv_tc32: encode Y failed (%d)", (int)r); return VPS_E_CUDA; }
+  }
+  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * T32_PLANES * e.b_plane_bytes + DCN32_SETUP_BYTES + 1024 + T32_BAR_BYTES +
+                   (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
   static bool smem_set = false;
   if (!smem_set) {
     if (cudaFuncSetAttribute(dcn_igemm_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       vps::set_error("deform_conv_tc32: cannot raise dynamic smem: %s", cudaGetErrorString(cudaGetLastError()));
       return VPS_E_CUDA;
     }
+    // a hint only: the driver picks the smallest carve-out that holds the launch's dynamic shared memory
+    cudaFuncSetAttribute(dcn_igemm_tc32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, smem <= 132 * 1024 ? 58 : 100);
+    (void)cudaGetLastError();
     smem_set = true;
   }
   const int grid = p.total_tiles < g_num_sms32 ? p.total_tiles : g_num_sms32;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T32_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(DCN32_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, dcn_igemm_tc32_kernel, tmB, p, e, d);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, dcn_igemm_tc32_kernel, tmB, tmY, p, e, d);
   if (le != cudaSuccess) { vps::set_error("deform_conv_tc32: launch failed: %s", cudaGetErrorString(le)); return VPS_E_CUDA; }
   VPS_CUDA_LAST("dcn_igemm_tc32_kernel");
   return VPS_OK;

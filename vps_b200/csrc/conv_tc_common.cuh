@@ -38,12 +38,16 @@ struct ConvTcParams {
   int oy_mul, oy_off, ox_mul, ox_off;
   const void* res;
   int res_cs, res_dtype, res_after_act, res_vec;
+  int epi_t;                   // tc32 kernels: coalesced (8x8-transposed) fp32 epilogue for full 32-channel chunks
   const float* bias;
   int cout;
   int act;
   float slope, out_scale;
 };
 
+#ifndef VPS_MBAR_SPIN_LOG2
+#define VPS_MBAR_SPIN_LOG2 26     // debugging builds: VPS_NVCC_EXTRA=-DVPS_MBAR_SPIN_LOG2=20 python -m vps_b200.build -f
+#endif
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -72,11 +76,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > (1u << 26)) {  // a lost arrival must fail loudly, never hang the GPU box
-      printf("vps conv_tc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
+    ++spins;                               // a lost arrival must fail loudly, never hang the GPU box: every stuck warp reports
+    if (spins == (1u << VPS_MBAR_SPIN_LOG2) && (threadIdx.x & 31) == 0)     // once, then the kernel is trapped
+      printf("vps conv_tc: mbarrier timeout block %d warp %d bar %u parity %u\n", blockIdx.x, threadIdx.x >> 5, bar, parity);
+    if (spins > (1u << VPS_MBAR_SPIN_LOG2) + (1u << (VPS_MBAR_SPIN_LOG2 - 2))) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
@@ -249,10 +252,28 @@ __device__ __forceinline__ void epi_chunk(const ConvTcParams& p, const uint32_t 
           if (j >= 8 * ng && j < nv) v[j] += __bfloat162float(rp[j]);
       }
     } else {
+      // fp32 residual: 256-bit / 128-bit loads (a scalar load per channel touches 32 different lines per warp instruction --
+      // 64 such instructions per tile cost more than the tile's MMAs: measured 17k clocks per 128x128 tile)
       const float* rp = (const float*)p.res + ro;
+      if (full && p.res_vec == 2) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nv) v[j] += rp[j];
+        for (int j = 0; j < 4; ++j) {
+          uint32_t raw[8];
+          ld_global_256(rp + 8 * j, raw);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[8 * j + t] += __uint_as_float(raw[t]);
+        }
+      } else if (full && p.res_vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 f = *reinterpret_cast<const float4*>(rp + 4 * j);
+          v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nv) v[j] += rp[j];
+      }
     }
   };
   if (has_res && !p.res_after_act) add_res();

@@ -593,3 +593,51 @@ extern "C" int vps_preprocess_u8(const uint8_t* bgr_hwc, int h, int w, const flo
   VPS_CUDA_LAST("preprocess_u8");
   return VPS_OK;
 }
+
+// ---------------------------------------------------------------- 3x3 convolutions with <= 3 output channels (predict_flow)
+// FlowNet2's predict_flow layers (submodules.py:27-28: Conv2d(cin, 2, 3, 1, 1), 19 launches per pair) have K = 9*cin up to
+// 9234 but N = 2: as implicit GEMMs they cost one K step per (tap, 32 channels) at any N.  They run as a 1x1 tensor-core
+// convolution with the taps moved to the output-channel axis, z[p][t*cout+co] = sum_c x[p][c] * w[co][c][t] (9x fewer K
+// steps, the input is read once instead of once per tap), followed by this gather:
+//     out[n,y,x,co] = act(bias[co] + sum_t z[n, y + t/3 - 1, x + t%3 - 1, t*cout + co]) * out_scale    (zero outside the map)
+namespace {
+template <int CO>
+__global__ void tap_gather3x3_kernel(vps::TV<const float> z, vps::TV<float> out, const float* __restrict__ bias, int act, float slope,
+                                     float out_scale) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= out.w) return;
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy < 0 || yy >= z.h || xx < 0 || xx >= z.w) continue;
+    const float* zp = z.p + z.off(n, yy, xx) + t * CO;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] += __ldg(zp + c);
+  }
+  float* op = out.p + out.off(n, y, x);
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    float v = acc[c];
+    if (bias) v += __ldg(bias + c);
+    op[c] = vps::apply_act(v, act, slope) * out_scale;
+  }
+}
+}  // namespace
+
+extern "C" int vps_tap_gather3x3(const vps_tensor* z, const vps_tensor* out, const float* bias, int act, float slope,
+                                 float out_scale, void* stream) {
+  VPS_CHECK_ARG(z->dtype == VPS_F32 && out->dtype == VPS_F32, "tap_gather3x3: fp32 tensors");
+  VPS_CHECK_ARG(out->c >= 1 && out->c <= 3 && z->c == 9 * out->c, "tap_gather3x3: z.c %d != 9 * out.c %d", z->c, out->c);
+  VPS_CHECK_ARG(z->n == out->n && z->h == out->h && z->w == out->w, "tap_gather3x3: shapes");
+  if (!((int64_t)out->n * out->h * out->w)) return VPS_OK;
+  dim3 grid((unsigned)vps::cdiv(out->w, 128), (unsigned)out->h, (unsigned)out->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out->c == 1) tap_gather3x3_kernel<1><<<grid, 128, 0, st>>>(vps::tv<const float>(*z), vps::tv<float>(*out), bias, act, slope, out_scale);
+  else if (out->c == 2) tap_gather3x3_kernel<2><<<grid, 128, 0, st>>>(vps::tv<const float>(*z), vps::tv<float>(*out), bias, act, slope, out_scale);
+  else tap_gather3x3_kernel<3><<<grid, 128, 0, st>>>(vps::tv<const float>(*z), vps::tv<float>(*out), bias, act, slope, out_scale);
+  VPS_CUDA_LAST("tap_gather3x3");
+  return VPS_OK;
+}

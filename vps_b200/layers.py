@@ -27,6 +27,13 @@ class Conv:
         self.stride, self.pad, self.act, self.slope = stride, pad, act, slope
         self.cout, self.cin = self.pk.cout, self.pk.cin
         self.k = self.pk.kh
+        # 3x3 / stride 1 / pad 1 layers with <= 3 output channels (FlowNet2 predict_flow*): in the tc32 precision they run as a
+        # 1x1 tensor-core convolution with the taps on the output-channel axis + a 9-tap gather (vps_tap_gather3x3): 9x fewer
+        # K steps than the 3x3 implicit GEMM, whose cost does not depend on N
+        self.pk_tap = None
+        if self.pk.kh == 3 and self.pk.kw == 3 and stride == 1 and pad == 1 and self.cout <= 3:
+            w = weight if scale is None else weight * scale.view(-1, 1, 1, 1)
+            self.pk_tap = PackedConv(w.permute(2, 3, 0, 1).reshape(9 * self.cout, self.cin, 1, 1).contiguous(), None)
 
     def out_hw(self, h, w):
         return ((h + 2 * self.pad - self.pk.kh) // self.stride + 1,
@@ -50,6 +57,12 @@ class Conv:
             xa = empty_nhwc(n, h, w, x.shape[3], x.dtype, x.device)
             ops.copy_scale(x, xa)
             x = xa
+        if (self.pk_tap is not None and res is None and x.dtype == torch.float32 and y.dtype == torch.float32
+                and ops.F32_TC[0] and self.tc_ok(x)):
+            z = empty_nhwc(n, h, w, 9 * self.cout, torch.float32, x.device)
+            ops.conv2d(x, self.pk_tap, z, use_tc=True)
+            ops.tap_gather3x3(z, y, self.pk.bias, act=act, slope=self.slope, out_scale=out_scale)
+            return y
         ops.conv2d(x, self.pk, y, stride=self.stride, pad=self.pad, act=act,
                    slope=self.slope, res=res, res_after_act=res_after_act, out_scale=out_scale,
                    use_tc=self.tc_ok(x))

@@ -541,3 +541,10 @@ def flow_deconv(x, w_host, b_host, y):
 def space_to_depth2(x, y):
     check(lib().vps_space_to_depth2(_bt(x), _bt(y), stream()), "space_to_depth2")
     return y
+
+
+def tap_gather3x3(z, out, bias, act=ACT_NONE, slope=0.1, out_scale=1.0):
+    """out = act(bias + sum over the 9 taps of the tap-major 1x1 result z) * out_scale (see vps_tap_gather3x3)"""
+    check(lib().vps_tap_gather3x3(_bt(z), _bt(out), _ptr(bias), act, C.c_float(slope), C.c_float(out_scale), stream()),
+          "tap_gather3x3")
+    return out
