@@ -89,11 +89,15 @@ def compare_frame(oracle, prod, img, ref, iid, device="cuda:0"):
     return rep, (o_res, ot), (p_res, pt)
 
 
-def near_tie_report(prod_map, oracle_map, oracle_logits, tol):
+def near_tie_report(prod_map, oracle_map, oracle_logits, tol, exclude=None):
     """Label maps of two correct fp32 implementations may differ where the argmax is decided by less than their logit
-    error.  Returns (pixels that differ, differing pixels NOT explained by an oracle top-2 logit margin <= tol)."""
+    error.  Returns (pixels that differ, differing pixels NOT explained by an oracle top-2 logit margin <= tol).
+    `exclude`: optional bool map of pixels left out of the comparison."""
     pm, om = prod_map.reshape(-1).long(), oracle_map.reshape(-1).long()
-    bad = (pm != om).nonzero().flatten()
+    diff = pm != om
+    if exclude is not None:
+        diff = diff & ~exclude.reshape(-1)
+    bad = diff.nonzero().flatten()
     if bad.numel() == 0:
         return 0, 0
     lg = oracle_logits.reshape(oracle_logits.shape[1], -1)[:, bad]          # [C, nbad]

