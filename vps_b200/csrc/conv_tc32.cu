@@ -40,7 +40,8 @@
 namespace {
 
 constexpr int T32_EPI_WARPS = 8;            // warps 8..15: two per TMEM lane quarter, alternating 32-column chunks
-constexpr int T32_CONV_WARPS = 5;           // warps 3..7 (warp 0 = TMA, warp 1 = main-product issuer, warp 2 = correction issuer)
+constexpr int T32_CONV_WARPS = 5;           // warps 3..7 (warp 0 = TMA, warp 1 = main-product issuer, warp 2 = correction issuer;
+                                            // VPS_TC32_SPLIT=1: warp 3 issues the corrections of the odd K steps, 4 converter warps)
 constexpr int T32_THREADS = 96 + 32 * (T32_EPI_WARPS + T32_CONV_WARPS);     // 512 = 4 warpgroups
 constexpr int T32_REGS_LOW = 64, T32_REGS_HIGH = 192;    // setmaxnreg: 256 * 64 + 256 * 192 = 65536
 constexpr int T32_KC = 32;                  // channels per K step: 64-byte operand rows (SWIZZLE_64B), 2 x K16
@@ -63,6 +64,8 @@ struct Tc32Extra {
   int group;                 // K steps of the main product accumulated inside the tensor core before promotion
   int dcn;                   // 1: the operand planes are produced by the deformable-sampling warps (no activation TMA)
   int nmain, ncorr, buf_cols;   // TMEM accumulator buffers: nmain group buffers, then ncorr correction buffers, buf_cols apart
+  int dbg;                      // timing experiments only (VPS_TC32_DBG): bit 0: skip A x B2, bit 1: skip A2 x B, bit 2: skip main
+  int corr_split;               // 1: the correction products of even / odd K steps are issued by two warps (2 and 3)
 };
 
 struct Dcn32Params {
@@ -193,7 +196,7 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
 }
 
 // ---------------------------------------------------------------- warps 2..7: fp32 box -> fp16 / bf16 / bf16 operand planes
-__device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, int ctid) {
+__device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, int ctid, int nthreads) {
   const int ntaps = p.kh * p.kw;
   const int items_per_tile = p.cin_chunks * (p.halo ? 1 : ntaps);
   const int tasks = e.rows * 4;                       // 8 channels (two 16-byte fp32 chunks) per task
@@ -206,7 +209,7 @@ __device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Ext
       mbar_wait(rg.pempty(as), aphase ^ 1);
       const uint32_t src = rg.s_base + ss * rg.s_bytes;
       const uint32_t dst = rg.a_base + as * rg.a_bytes;
-      for (int task = ctid; task < tasks; task += 32 * T32_CONV_WARPS) {
+      for (int task = ctid; task < tasks; task += nthreads) {
         const int r = task >> 2, j = task & 3;
         // staging rows are 128 bytes, SWIZZLE_128B (written by TMA): 16-byte chunk c of row r sits at chunk c ^ (r & 7)
         const uint32_t row_s = src + (uint32_t)r * 128u;
@@ -380,7 +383,11 @@ __device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo) { return (sbo >> 4) 
 
 // ROLE 0: main product (stats slots [0] group-buffer wait, [1] planes, [2] weights, [4] total); ROLE 1: corrections
 // (stats [3] correction-buffer wait)
-template <int ROLE, bool HALO, bool STATS>
+// PAR (ROLE 1 only): -1 = this warp issues every K step; 0 / 1 = it issues the even / odd steps of a tile and only keeps the
+// ring bookkeeping of the others.  The issue loops are bound by the latency of their dependent instructions (ncu: ~130 per
+// step for the corrections at ~8 clocks each -- with EVERY tcgen05.mma removed the kernel is only 10 % faster), so the
+// per-step work of the slowest role is halved by alternating steps between two warps.
+template <int ROLE, bool HALO, bool STATS, int PAR = -1>
 __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base) {
   const uint32_t idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);   // D = f32, A = B = f16
   const int ntaps = p.kh * p.kw, kw = p.kw;
@@ -395,68 +402,98 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
   int as = 0, bs = 0, tb = 0;
   uint32_t aphase = 0, bphase = 0, tphase = 0;       // tphase: one parity bit per TMEM buffer of this role
   uint32_t nstep = 0;                                // K steps issued so far (all tiles)
-  const uint32_t sync_addr = rg.issue_sync();
+  const uint32_t sync_addr = rg.issue_sync(), sync2_addr = sync_addr + 4u;
   long long w_t = 0, w_a = 0, w_b = 0;
   const long long t_begin = STATS ? clock64() : 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     int in_group = 0;
     uint32_t d_tmem = 0, first = 0;
+    uint32_t par = 0;                                // parity of the step inside the tile
+    bool tile_waited = false;
     for (int cc = 0; cc <= last_cc; ++cc) {
       const bool two = cc != last_cc || e.nk_last > 1;
       uint32_t a16 = 0;
       int sx = 0;
-      for (int tap = 0; tap < ntaps; ++tap) {
+      bool a_waited = false;
+      for (int tap = 0; tap < ntaps; ++tap, par ^= 1u) {
         const bool last_step = cc == last_cc && tap == ntaps - 1;
-        if (ROLE == 0 ? in_group == 0 : (cc == 0 && tap == 0)) {
+        const bool mine = PAR < 0 || par == (uint32_t)PAR;
+        // the last step of the tile / last tap of the chunk THIS warp issues (the other parity owns the very last one
+        // every second time); a split is only configured for tiles of >= 2 steps
+        const bool my_last_step = PAR < 0 ? last_step : (last_step ? mine : (mine && cc == last_cc && tap == ntaps - 2 && ntaps >= 2) ||
+                                                                             (mine && ntaps == 1 && cc == last_cc - 1));
+        ++nstep;
+        if (ROLE == 0 ? in_group == 0 : (PAR < 0 ? (cc == 0 && tap == 0) : (mine && !tile_waited))) {
           // ROLE 0: a new group of the main product starts on a drained buffer with accumulate = 0
           // ROLE 1: the tile's correction buffer must have been drained by the promotion warps
           const long long t0 = STATS ? clock64() : 0;
           mbar_wait(ROLE == 0 ? rg.gempty(tb) : rg.cempty(tb), ((tphase >> tb) & 1u) ^ 1u);
           if (STATS) w_t += clock64() - t0;
           d_tmem = buf0 + (uint32_t)tb * buf_cols;
-          first = 0;
+          first = (ROLE == 1 && PAR == 1) ? 1u : 0u;       // the odd warp never starts the tile's accumulation
+          tile_waited = true;
         }
-        if (!HALO || tap == 0) {
+        if (HALO ? (tap == 0) : true) a16 = a_base16 + (uint32_t)as * a_bytes16;
+        const bool item_done = !HALO || tap == ntaps - 1;
+        // last tap of this chunk issued by this warp: its commit releases the operand planes
+        const bool my_item_done = !HALO ? mine : (PAR < 0 ? item_done : (item_done ? mine : (mine && tap == ntaps - 2)));
+        if (mine) {
+        if (ROLE == 1) {
+          // the tensor pipe executes MMAs in issue order: a correction issuer that ran ahead (it never waits for a group
+          // buffer) would queue several steps of its 4-MMA batches in front of the main product and stretch the latency of
+          // every promoted group -- it issues step s only after the main-product warp has issued step s; the odd warp also
+          // follows the even warp's previous step (whose first MMA of a tile resets the accumulator).  This comes BEFORE the
+          // barrier waits: a warp that skips every other use of a ring slot re-visits the slot's barrier two phases later with
+          // the same parity, and only the fact that the main warp (which waits on every phase) is already past this step
+          // makes that wait unambiguous.
+          uint32_t seen;
+          do {
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(sync_addr) : "memory");
+          } while ((int32_t)(seen - nstep) < 0);
+          if (PAR == 1) {
+            do {
+              asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(sync2_addr) : "memory");
+            } while ((int32_t)(seen - (nstep - 1u)) < 0);
+          }
+        }
+        if (HALO ? !a_waited : true) {
           const long long t0 = STATS ? clock64() : 0;
           mbar_wait(rg.pfull(as), aphase);
           if (STATS) w_a += clock64() - t0;
-          a16 = a_base16 + (uint32_t)as * a_bytes16;
+          a_waited = true;
         }
         {
           const long long t0 = STATS ? clock64() : 0;
           mbar_wait(rg.bfull(bs), bphase);
           if (STATS) w_b += clock64() - t0;
         }
-        ++nstep;
-        if (ROLE == 1) {
-          // the tensor pipe executes MMAs in issue order: a correction issuer that ran ahead (it never waits for a group
-          // buffer) would queue several steps of its 4-MMA batches in front of the main product and stretch the latency of
-          // every promoted group -- it issues step s only after the main-product warp has issued step s
-          uint32_t seen;
-          do {
-            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(sync_addr) : "memory");
-          } while ((int32_t)(seen - nstep) < 0);
-        }
         tc_fence_after();
-        const bool item_done = !HALO || tap == ntaps - 1;
+        }
         const bool close = ROLE == 0 ? (++in_group == G || last_step) : last_step;
         const uint32_t b16 = b_base16 + (uint32_t)bs * b_bytes16;
-        if (elect_one()) {
+        if (mine && elect_one()) {
           if (ROLE == 0) {                 // main: A x B
+            if (!(e.dbg & 4)) {
             umma_f16_lohi(d_tmem, a16, a_hi, b16, b_hi, idesc, first);
             if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + 2, b_hi, idesc, 1u);
+            }
             asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sync_addr), "r"(nstep) : "memory");
           } else {                         // corrections: A2 x B + A x B2 (scaled by 2^-11 when the buffer is added)
+            if (!(e.dbg & 2)) {
             umma_f16_lohi(d_tmem, a16 + a_plane16, a_hi, b16, b_hi, idesc, first);
             if (two) umma_f16_lohi(d_tmem, a16 + a_plane16 + 2, a_hi, b16 + 2, b_hi, idesc, 1u);
+            }
+            if (!(e.dbg & 1)) {
             umma_f16_lohi(d_tmem, a16, a_hi, b16 + b_plane16, b_hi, idesc, 1u);
             if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + b_plane16 + 2, b_hi, idesc, 1u);
+            }
           }
+          if (ROLE == 1 && PAR == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sync2_addr), "r"(nstep) : "memory");
           umma_commit(rg.bempty(bs));
-          if (item_done) umma_commit(rg.pempty(as));
-          if (close) umma_commit(ROLE == 0 ? rg.gfull(tb) : rg.cfull(tb));
+          if (my_item_done) umma_commit(rg.pempty(as));
+          if (ROLE == 0 ? close : my_last_step) umma_commit(ROLE == 0 ? rg.gfull(tb) : rg.cfull(tb));
         }
-        first = 1;
+        if (mine) first = 1;
         if (close) {
           tphase ^= 1u << tb;
           if (++tb == nbuf) tb = 0;
@@ -478,12 +515,12 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
   }
 }
 
-template <int ROLE>
+template <int ROLE, int PAR = -1>
 __device__ __forceinline__ void mma32_dispatch(const ConvTcParams& p, const Tc32Extra& e, const Ring32& rg, uint32_t tmem_base) {
   if (p.stats) {
-    if (p.halo) mma32<ROLE, true, true>(p, e, rg, tmem_base); else mma32<ROLE, false, true>(p, e, rg, tmem_base);
+    if (p.halo) mma32<ROLE, true, true, PAR>(p, e, rg, tmem_base); else mma32<ROLE, false, true, PAR>(p, e, rg, tmem_base);
   } else {
-    if (p.halo) mma32<ROLE, true, false>(p, e, rg, tmem_base); else mma32<ROLE, false, false>(p, e, rg, tmem_base);
+    if (p.halo) mma32<ROLE, true, false, PAR>(p, e, rg, tmem_base); else mma32<ROLE, false, false, PAR>(p, e, rg, tmem_base);
   }
 }
 
@@ -616,8 +653,14 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
   const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
   const int c0a = half * 32, c0b = (half + 2) * 32;          // this warp's two 32-column chunks
   const bool has_a = c0a < bn, has_b = c0b < bn;
-  const uint32_t scratch = scratch_base + (uint32_t)(warp - 8) * 4096u;
-  int gb = 0, cb = 0;
+  uint32_t scratch = scratch_base + (uint32_t)(warp - 8) * 4096u;
+  // Loop-invariant addresses live in registers the compiler cannot re-derive: left alone it rematerialises them from the kernel
+  // parameters (shared-memory window base via S2UR, ring sizes via LDCU / UIMAD: a dozen dependent uniform-datapath
+  // instructions in front of every barrier operation), and this role is bound by its dependent-instruction latency.
+  uint32_t gfull0 = rg.gfull(0), lane_base_r = lane_base, buf_cols_r = (uint32_t)e.buf_cols, nmain_r = (uint32_t)e.nmain;
+  asm volatile("" : "+r"(gfull0), "+r"(lane_base_r), "+r"(buf_cols_r), "+r"(nmain_r), "+r"(scratch));
+  constexpr uint32_t GEMPTY_OFF = 8u * T32_MAX_MAIN;
+  uint32_t gb = 0, cb = 0;
   uint32_t gphase = 0, cphase = 0;
   constexpr bool st = STATS;
   long long w_g = 0, t_store = 0;
@@ -625,10 +668,11 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
     float sum[2][32];
     for (int g = 0; g < ngroups; ++g) {
       const long long t0 = st ? clock64() : 0;
-      mbar_wait(rg.gfull(gb), (gphase >> gb) & 1u);
+      const uint32_t gf = gfull0 + 8u * gb;
+      mbar_wait(gf, (gphase >> gb) & 1u);
       if (st) w_g += clock64() - t0;
       tc_fence_after();
-      const uint32_t t_row = lane_base + (uint32_t)(gb * e.buf_cols);
+      const uint32_t t_row = lane_base_r + gb * buf_cols_r;
       // one 32-column chunk in flight at a time: with both (64 staging registers next to the 64 running sums) ptxas spills ~35
       // sums around every tcgen05.ld even at 192 registers (re-measured with the TMA epilogue); the buffer is released before
       // the last chunk's adds
@@ -650,7 +694,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(rg.gempty(gb));     // one arrival per warp (256 per-thread arrivals on one mbarrier serialise)
+      if (lane == 0) mbar_arrive(gf + GEMPTY_OFF);   // one arrival per warp (256 per-thread arrivals on one mbarrier serialise)
       if (has_b) {
         if (g == 0) {
 #pragma unroll
@@ -661,13 +705,14 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
         }
       }
       gphase ^= 1u << gb;
-      if (++gb == e.nmain) gb = 0;
+      if (++gb == nmain_r) gb = 0;
     }
     // ---- the tile's correction products
-    mbar_wait(rg.cfull(cb), (cphase >> cb) & 1u);
+    const uint32_t cf = gfull0 + 8u * (2u * T32_MAX_MAIN) + 8u * cb;       // cfull(cb); cempty(cb) = cf + 16
+    mbar_wait(cf, (cphase >> cb) & 1u);
     tc_fence_after();
     {
-      const uint32_t t_row = lane_base + (uint32_t)((e.nmain + cb) * e.buf_cols);
+      const uint32_t t_row = lane_base_r + (nmain_r + cb) * buf_cols_r;
       uint32_t r[32];
       if (has_a) {
         tmem_ld32(t_row + (uint32_t)c0a, r);
@@ -681,14 +726,14 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(rg.cempty(cb));
+      if (lane == 0) mbar_arrive(cf + 16u);
       if (has_b) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum[1][j] = __fmaf_rn(__uint_as_float(r[j]), T32_LO_INV, sum[1][j]);
       }
     }
     cphase ^= 1u << cb;
-    if (++cb == e.ncorr) cb = 0;
+    if (++cb == (uint32_t)e.ncorr) cb = 0;
     const long long t1 = st ? clock64() : 0;
     // ---- bias / activation / residual / store of this tile
     const int prob = tile / p.tiles_per_prob;
@@ -737,8 +782,10 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 2) {
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
-      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * T32_CONV_WARPS;      // sempty, pfull: every converter thread
-      if ((i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) || (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES)) count = 2;   // pempty, bempty: both issuers
+      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * (e.corr_split ? 4 : 5);      // sempty, pfull: every converter thread
+      if (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES) count = 2;                    // bempty: the main and ONE correction issuer
+      if (i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) count = (p.halo && e.corr_split) ? 3 : 2;      // pempty: halo planes feed all taps
+      if (i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2) count = e.corr_split ? 2 : 1;   // cfull
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
         count = T32_EPI_WARPS;                                                    // gempty, cempty: one arrival per promotion warp
       mbar_init(rg.bar_base + 8u * i, count);
@@ -750,6 +797,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (p.epi_t == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY.m[0]) : "memory");
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync()), "r"(0u) : "memory");
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync() + 4u), "r"(0u) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rg.tmem_slot()), "r"((uint32_t)TMEM_COLS)
@@ -770,8 +818,9 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T32_REGS_LOW));
     if (warp == 0) producer32(p, e, rg, &tmA, &tmB);
     else if (warp == 1) mma32_dispatch<0>(p, e, rg, tmem_base);
-    else if (warp == 2) mma32_dispatch<1>(p, e, rg, tmem_base);
-    else converter32(p, e, rg, (int)threadIdx.x - 96);
+    else if (warp == 2) { if (e.corr_split) mma32_dispatch<1, 0>(p, e, rg, tmem_base); else mma32_dispatch<1>(p, e, rg, tmem_base); }
+    else if (warp == 3 && e.corr_split) mma32_dispatch<1, 1>(p, e, rg, tmem_base);
+    else converter32(p, e, rg, (int)threadIdx.x - (e.corr_split ? 128 : 96), e.corr_split ? 128 : 160);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T32_REGS_HIGH));
     if (p.stats) {     // debugging aid (VPS_CONV_STATS=1): clocks of the generic path only
@@ -1039,6 +1088,13 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   static int group_env = -1;
   if (group_env < 0) { const char* ev = getenv("VPS_TC32_GROUP"); group_env = ev ? atoi(ev) : 1; }
   e.group = group_env < 1 ? 1 : group_env;
+  { static int dbg_env = -1; if (dbg_env < 0) { const char* ev = getenv("VPS_TC32_DBG"); dbg_env = ev ? atoi(ev) : 0; } e.dbg = dbg_env; }
+  {
+    static int split_env = -1;
+    // measured neutral (fat layers 0.605 -> 0.609 ms, thin layers +2 %): the corrections issuer is not the pacing role; off
+    if (split_env < 0) { const char* ev = getenv("VPS_TC32_SPLIT"); split_env = ev ? atoi(ev) : 0; }
+    e.corr_split = (split_env && p.cin_chunks * ntaps >= 2) ? 1 : 0;
+  }
   e.buf_cols = block_n <= 64 ? 64 : 128;
   // 128-column buffers: long tiles want a third group buffer (slack for the promotion latency), short tiles (1x1 layers
   // with few K steps) a second correction buffer so that the next tile can start while this one is stored
