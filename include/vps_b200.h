@@ -139,6 +139,13 @@ int vps_correlation_tc(const vps_tensor* f1, const vps_tensor* f2, const vps_ten
                        int max_disp, int stride1, int stride2, int act, float slope, void* stream);
 int vps_correlation_simt(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad,
                          int max_disp, int stride1, int stride2, int act, float slope, void* stream);
+/* correlation of fp32 features on the tensor cores in the parity precision (tc32): operands split into fp16 planes
+ * (v = hi + 2^-11 lo), three banded-GEMM passes (hi.hi + 2^-11 (hi.lo + lo.hi)) accumulated in the fp32 output.  Same call sites /
+ * geometries as vps_correlation_tc (correlation_cuda.cc:10-87); ws = vps_correlation_tc32_ws_bytes(f1) bytes, 256-byte aligned. */
+int64_t vps_correlation_tc32_ws_bytes(const vps_tensor* f1);
+int vps_correlation_tc32(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad, int max_disp, int stride1,
+                         int stride2, int act, float slope, void* ws, void* stream);
+
 /* resample2d_cuda.forward (resample2d_cuda.cc:6-31, resample2d_kernel.cu:16-71): bilinear warp by
  * pixel-unit flow (channel 0 = x), border-clamped taps, kernel_size 1. */
 int vps_resample2d(const vps_tensor* src, const vps_tensor* flow, const vps_tensor* out, void* stream);

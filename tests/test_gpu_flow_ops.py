@@ -117,3 +117,33 @@ def test_flownet_glue_fused_equals_separate_ops(cuda, dtype):
     torch.cuda.synchronize()
     assert torch.equal(got3.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
                        ref3.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
+
+
+@pytest.mark.parametrize("cfg", [(20, 2, 256, 40, 72), (4, 1, 256, 33, 31), (20, 2, 64, 37, 53), (4, 1, 128, 21, 50)])
+def test_correlation_tc32(cuda, cfg):
+    """fp32 features on the tensor cores (split fp16 planes, three banded-GEMM passes) vs the fp32 oracle: fp32-class error
+    (the single bf16 pass on the same features is off by ~1e-2), slice neighbours untouched, no saturation"""
+    from oracle import ops as O
+    from vps_b200 import ops
+    md, s2, C, H, W = cfg
+    g = torch.Generator().manual_seed(23)
+    f1 = torch.randn(1, C, H, W, generator=g)
+    f2 = torch.randn(1, C, H, W, generator=g)
+    ref = torch.nn.functional.leaky_relu(O.correlation(f1, f2, md, 1, md, 1, s2), 0.1)
+    D = 2 * (md // s2) + 1
+    cs = (D * D + 7) // 8 * 8
+    buf = torch.full((1, H, W, cs + 8), 7.0, dtype=torch.float32, device=cuda)
+    out = buf[..., 8:8 + D * D]
+    old = ops.F32_TC[0]
+    ops.F32_TC[0] = True
+    try:
+        n0 = ops.launch_count()
+        ops.correlation(_nhwc(f1).to(cuda), _nhwc(f2).to(cuda), out, md, md, 1, s2, act=ops.ACT_LRELU, slope=0.1, impl="tc32")
+        assert ops.launch_count() - n0 == 5          # 2 operand splits + 3 tensor-core passes
+    finally:
+        ops.F32_TC[0] = old
+    torch.cuda.synchronize()
+    got = out.cpu().permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item()), cfg
+    assert (buf[..., :8] == 7.0).all() and (buf[..., 8 + D * D:] == 7.0).all()
+    assert ops.tc32_overflow() == 0

@@ -49,6 +49,7 @@ def lib():
         _lib.vps_launch_count.restype = C.c_int64
         _lib.vps_packed_tc_bytes.restype = C.c_int64
         _lib.vps_packed_tc32_bytes.restype = C.c_int64
+        _lib.vps_correlation_tc32_ws_bytes.restype = C.c_int64
         _lib.vps_unify_pan_ws_bytes.restype = C.c_int64
         _lib.vps_unify_pan_error_offset.restype = C.c_int64
         _lib.vps_tube_confusion_ws_bytes.restype = C.c_int64
@@ -69,7 +70,7 @@ EXPORTS = [
     "vps_conv2d_tc", "vps_conv2d_tc_multi", "vps_conv2d_simt", "vps_pack_weights_tc", "vps_pack_weights_simt",
     "vps_packed_tc_bytes", "vps_im2col",
     "vps_conv2d_tc32", "vps_conv2d_tc32_multi", "vps_pack_weights_tc32", "vps_packed_tc32_bytes", "vps_tc32_overflow", "vps_deform_conv_tc32",
-    "vps_correlation", "vps_correlation_tc", "vps_correlation_simt", "vps_resample2d", "vps_channelnorm", "vps_flownet_input", "vps_flownet_stage", "vps_flownet_cat3", "vps_flow_deconv",
+    "vps_correlation", "vps_correlation_tc", "vps_correlation_simt", "vps_correlation_tc32", "vps_correlation_tc32_ws_bytes", "vps_resample2d", "vps_channelnorm", "vps_flownet_input", "vps_flownet_stage", "vps_flownet_cat3", "vps_flow_deconv",
     "vps_nchw_to_nhwc", "vps_nhwc_to_nchw", "vps_copy_scale", "vps_axpby",
     "vps_space_to_depth2", "vps_tap_gather3x3", "vps_preprocess_u8", "vps_resize_bilinear", "vps_resize_nearest", "vps_pool2d", "vps_groupnorm",
     "vps_bfp_gather", "vps_bfp_scatter", "vps_flow_warp", "vps_tcea_temporal", "vps_tcea_combine",

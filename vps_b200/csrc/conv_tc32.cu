@@ -66,6 +66,10 @@ struct Tc32Extra {
   int nmain, ncorr, buf_cols;   // TMEM accumulator buffers: nmain group buffers, then ncorr correction buffers, buf_cols apart
   int dbg;                      // timing experiments only (VPS_TC32_DBG): bit 0: skip A x B2, bit 1: skip A2 x B, bit 2: skip main
   int corr_split;               // 1: the correction products of even / odd K steps are issued by two warps (2 and 3)
+  int sleep_ns;                 // back-off of the converter / producer waits (VPS_TC32_SLEEP, default 0 = poll)
+  int split4;                   // 1 (implies corr_split; halo mode, group = 1, even nmain): the main product too is issued by two
+                                //    warps (1 and 4), even / odd K steps counted over the whole CTA -> each owns the group buffers
+                                //    of its parity
 };
 
 struct Dcn32Params {
@@ -139,6 +143,38 @@ __device__ __forceinline__ float to_f16_sat(float v, unsigned short& bits, bool&
   return __half2float(__ushort_as_half(h));
 }
 
+// operand split of two values at once: hi = packed fp16x2 of (v0, v1) (round to nearest, saturating), lo = packed fp16x2 of
+// 2^11 * (v - fp16(v)).  Same values as two to_f16_sat() pairs with 10 instead of 14 instructions (the converter and the
+// deformable sampler are bound by exactly this arithmetic).
+__device__ __forceinline__ void split_pair_f16(float v0, float v1, uint32_t& hi, uint32_t& lo, bool& over) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));       // first source -> upper half
+  over = over || !(fabsf(v0) <= 65504.f) || !(fabsf(v1) <= 65504.f);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float r0 = (v0 - h.x) * T32_LO_SCALE, r1 = (v1 - h.y) * T32_LO_SCALE;          // exact in fp32
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+// debugging aid (VPS_CONV_TRACE=1): clock of event `ev` at K step `step` of CTA 0
+__device__ __forceinline__ void trace_ev(const ConvTcParams& p, int ev, uint32_t step) {
+  if (p.trace && blockIdx.x == 0 && step < 256u && (threadIdx.x & 31) == 0) p.trace[ev * 256 + step] = clock64();
+}
+
+// wait with back-off for roles with slack (converters, TMA producer): a failed poll sleeps instead of re-polling at once, so
+// that the idle warps' polling does not queue in front of the latency-critical issuers' shared-memory / barrier operations
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (ns) __nanosleep(ns);
+    if (++spins > (1u << VPS_MBAR_SPIN_LOG2)) {
+      if ((threadIdx.x & 31) == 0) printf("vps conv_tc32: mbarrier timeout (relaxed wait) block %d warp %d bar %u\n", blockIdx.x, threadIdx.x >> 5, bar);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- tile walk shared by the roles
 struct TileCoord {
   int prob, n_idx, img, ty, tx;
@@ -165,7 +201,7 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
   const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes, b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
   const int bn = p.block_n;
   int ss = 0, bs = 0;
-  uint32_t sphase = 0, bphase = 0;
+  uint32_t sphase = 0, bphase = 0, pstep = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = tile_coord(p, tile);
     const int x_base = t.tx * p.tw * p.sw - p.pw_[t.prob];
@@ -175,7 +211,7 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
       int r = 0, s = 0;
       for (int tap = 0; tap < ntaps; ++tap) {
         if (!e.dcn && (!halo || tap == 0)) {
-          mbar_wait(rg.sempty(ss), sphase ^ 1);
+          mbar_wait_relaxed(rg.sempty(ss), sphase ^ 1, (uint32_t)e.sleep_ns);
           if (elect_one()) {
             mbar_expect_tx(rg.sfull(ss), a_box_bytes);
             tma_load_4d(rg.s_base + ss * rg.s_bytes, tmA, rg.sfull(ss), cc * T32_KC, halo ? x_base : x_base + s,
@@ -183,7 +219,8 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
           }
           if (++ss == T32_STAGE_SLOTS) { ss = 0; sphase ^= 1; }
         }
-        mbar_wait(rg.bempty(bs), bphase ^ 1);
+        mbar_wait_relaxed(rg.bempty(bs), bphase ^ 1, (uint32_t)e.sleep_ns);
+        trace_ev(p, 0, pstep++);
         if (elect_one()) {     // both weight planes of this (tap, chunk) in one 5-D box
           mbar_expect_tx(rg.bfull(bs), b_bytes);
           tma_load_5d(rg.b_base + bs * rg.b_bytes, tmB, rg.bfull(bs), cc * T32_KC, n0, tap, t.prob, 0);
@@ -205,8 +242,8 @@ __device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Ext
   bool over = false;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     for (int it = 0; it < items_per_tile; ++it) {
-      mbar_wait(rg.sfull(ss), sphase);
-      mbar_wait(rg.pempty(as), aphase ^ 1);
+      mbar_wait_relaxed(rg.sfull(ss), sphase, (uint32_t)e.sleep_ns);
+      mbar_wait_relaxed(rg.pempty(as), aphase ^ 1, (uint32_t)e.sleep_ns);
       const uint32_t src = rg.s_base + ss * rg.s_bytes;
       const uint32_t dst = rg.a_base + as * rg.a_bytes;
       for (int task = ctid; task < tasks; task += nthreads) {
@@ -219,22 +256,14 @@ __device__ __forceinline__ void converter32(const ConvTcParams& p, const Tc32Ext
                      : "r"(row_s + (((uint32_t)(2 * j) ^ sw) << 4)));
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                      : "r"(row_s + (((uint32_t)(2 * j + 1) ^ sw) << 4)));
-        unsigned short hb[8], lb[8];
+        uint32_t hp[4], lp[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float lo = v[q] - to_f16_sat(v[q], hb[q], over);     // exact in fp32, |lo| <= half an fp16 ulp of v
-          bool dummy = false;
-          to_f16_sat(lo * T32_LO_SCALE, lb[q], dummy);
-        }
+        for (int q = 0; q < 4; ++q) split_pair_f16(v[2 * q], v[2 * q + 1], hp[q], lp[q], over);
         // operand planes: 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
         const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
         const uint32_t pm = dst + off, pl = pm + (uint32_t)e.plane_bytes;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"((uint32_t)hb[0] | ((uint32_t)hb[1] << 16)),
-                     "r"((uint32_t)hb[2] | ((uint32_t)hb[3] << 16)), "r"((uint32_t)hb[4] | ((uint32_t)hb[5] << 16)),
-                     "r"((uint32_t)hb[6] | ((uint32_t)hb[7] << 16)) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"((uint32_t)lb[0] | ((uint32_t)lb[1] << 16)),
-                     "r"((uint32_t)lb[2] | ((uint32_t)lb[3] << 16)), "r"((uint32_t)lb[4] | ((uint32_t)lb[5] << 16)),
-                     "r"((uint32_t)lb[6] | ((uint32_t)lb[7] << 16)) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
       }
       mbar_arrive(rg.sempty(ss));                                        // staging slot may be refilled
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> tensor-core reads
@@ -331,22 +360,15 @@ __device__ __forceinline__ void dcn_gather32(const ConvTcParams& p, const Tc32Ex
           acc[0] += wq[c] * v0[c].x; acc[1] += wq[c] * v0[c].y; acc[2] += wq[c] * v0[c].z; acc[3] += wq[c] * v0[c].w;
           acc[4] += wq[c] * v1[c].x; acc[5] += wq[c] * v1[c].y; acc[6] += wq[c] * v1[c].z; acc[7] += wq[c] * v1[c].w;
         }
-        unsigned short hb[8], lb[8];
-        bool over = false, dummy = false;
+        uint32_t hp[4], lp[4];
+        bool over = false;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float lo = acc[q] - to_f16_sat(acc[q], hb[q], over);
-          to_f16_sat(lo * T32_LO_SCALE, lb[q], dummy);
-        }
+        for (int q = 0; q < 4; ++q) split_pair_f16(acc[2 * q], acc[2 * q + 1], hp[q], lp[q], over);
         if (over) atomicAdd(&g_tc32_overflow, 1u);
         const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)j) ^ ((uint32_t)(r >> 1) & 3u)) << 4);
         const uint32_t pm = dst + off, pl = pm + (uint32_t)e.plane_bytes;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"((uint32_t)hb[0] | ((uint32_t)hb[1] << 16)),
-                     "r"((uint32_t)hb[2] | ((uint32_t)hb[3] << 16)), "r"((uint32_t)hb[4] | ((uint32_t)hb[5] << 16)),
-                     "r"((uint32_t)hb[6] | ((uint32_t)hb[7] << 16)) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"((uint32_t)lb[0] | ((uint32_t)lb[1] << 16)),
-                     "r"((uint32_t)lb[2] | ((uint32_t)lb[3] << 16)), "r"((uint32_t)lb[4] | ((uint32_t)lb[5] << 16)),
-                     "r"((uint32_t)lb[6] | ((uint32_t)lb[7] << 16)) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pm), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pl), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core reads
       __syncwarp();
@@ -402,7 +424,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
   int as = 0, bs = 0, tb = 0;
   uint32_t aphase = 0, bphase = 0, tphase = 0;       // tphase: one parity bit per TMEM buffer of this role
   uint32_t nstep = 0;                                // K steps issued so far (all tiles)
-  const uint32_t sync_addr = rg.issue_sync(), sync2_addr = sync_addr + 4u;
+  const uint32_t sync_addr = rg.issue_sync(), sync2_addr = sync_addr + 8u;      // [main even | main odd], [corrections even]
   long long w_t = 0, w_a = 0, w_b = 0;
   const long long t_begin = STATS ? clock64() : 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -417,18 +439,22 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
       bool a_waited = false;
       for (int tap = 0; tap < ntaps; ++tap, par ^= 1u) {
         const bool last_step = cc == last_cc && tap == ntaps - 1;
-        const bool mine = PAR < 0 || par == (uint32_t)PAR;
+        // ownership: corrections by the parity of the step inside the tile (step 0 resets the tile's accumulator), the main
+        // product by the parity of the CTA-wide step count (= the parity of its group buffer: nmain is even when it is split)
+        const uint32_t gpar = nstep & 1u;
+        const bool mine = PAR < 0 || (ROLE == 0 ? gpar == (uint32_t)PAR : par == (uint32_t)PAR);
         // the last step of the tile / last tap of the chunk THIS warp issues (the other parity owns the very last one
         // every second time); a split is only configured for tiles of >= 2 steps
         const bool my_last_step = PAR < 0 ? last_step : (last_step ? mine : (mine && cc == last_cc && tap == ntaps - 2 && ntaps >= 2) ||
                                                                              (mine && ntaps == 1 && cc == last_cc - 1));
         ++nstep;
-        if (ROLE == 0 ? in_group == 0 : (PAR < 0 ? (cc == 0 && tap == 0) : (mine && !tile_waited))) {
+        if (ROLE == 0 ? (in_group == 0 && mine) : (PAR < 0 ? (cc == 0 && tap == 0) : (mine && !tile_waited))) {
           // ROLE 0: a new group of the main product starts on a drained buffer with accumulate = 0
           // ROLE 1: the tile's correction buffer must have been drained by the promotion warps
           const long long t0 = STATS ? clock64() : 0;
           mbar_wait(ROLE == 0 ? rg.gempty(tb) : rg.cempty(tb), ((tphase >> tb) & 1u) ^ 1u);
           if (STATS) w_t += clock64() - t0;
+          if (STATS && ROLE == 0) trace_ev(p, 1, nstep - 1u);
           d_tmem = buf0 + (uint32_t)tb * buf_cols;
           first = (ROLE == 1 && PAR == 1) ? 1u : 0u;       // the odd warp never starts the tile's accumulation
           tile_waited = true;
@@ -447,8 +473,9 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           // the same parity, and only the fact that the main warp (which waits on every phase) is already past this step
           // makes that wait unambiguous.
           uint32_t seen;
+          const uint32_t main_ctr = sync_addr + (e.split4 ? 4u * gpar : 0u);      // split main product: one counter per parity
           do {
-            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(sync_addr) : "memory");
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(main_ctr) : "memory");
           } while ((int32_t)(seen - nstep) < 0);
           if (PAR == 1) {
             do {
@@ -466,6 +493,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           const long long t0 = STATS ? clock64() : 0;
           mbar_wait(rg.bfull(bs), bphase);
           if (STATS) w_b += clock64() - t0;
+          if (STATS) trace_ev(p, ROLE == 0 ? 2 : 4, nstep - 1u);
         }
         tc_fence_after();
         }
@@ -477,7 +505,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
             umma_f16_lohi(d_tmem, a16, a_hi, b16, b_hi, idesc, first);
             if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + 2, b_hi, idesc, 1u);
             }
-            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sync_addr), "r"(nstep) : "memory");
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sync_addr + (PAR == 1 ? 4u : 0u)), "r"(nstep) : "memory");
           } else {                         // corrections: A2 x B + A x B2 (scaled by 2^-11 when the buffer is added)
             if (!(e.dbg & 2)) {
             umma_f16_lohi(d_tmem, a16 + a_plane16, a_hi, b16, b_hi, idesc, first);
@@ -494,6 +522,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           if (ROLE == 0 ? close : my_last_step) umma_commit(ROLE == 0 ? rg.gfull(tb) : rg.cfull(tb));
         }
         if (mine) first = 1;
+        if (STATS && mine) trace_ev(p, ROLE == 0 ? 3 : 5, nstep - 1u);
         if (close) {
           tphase ^= 1u << tb;
           if (++tb == nbuf) tb = 0;
@@ -660,7 +689,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
   uint32_t gfull0 = rg.gfull(0), lane_base_r = lane_base, buf_cols_r = (uint32_t)e.buf_cols, nmain_r = (uint32_t)e.nmain;
   asm volatile("" : "+r"(gfull0), "+r"(lane_base_r), "+r"(buf_cols_r), "+r"(nmain_r), "+r"(scratch));
   constexpr uint32_t GEMPTY_OFF = 8u * T32_MAX_MAIN;
-  uint32_t gb = 0, cb = 0;
+  uint32_t gb = 0, cb = 0, pgroup = 0;
   uint32_t gphase = 0, cphase = 0;
   constexpr bool st = STATS;
   long long w_g = 0, t_store = 0;
@@ -671,6 +700,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       const uint32_t gf = gfull0 + 8u * gb;
       mbar_wait(gf, (gphase >> gb) & 1u);
       if (st) w_g += clock64() - t0;
+      if (st && warp == 8) trace_ev(p, 6, pgroup);
       tc_fence_after();
       const uint32_t t_row = lane_base_r + gb * buf_cols_r;
       // one 32-column chunk in flight at a time: with both (64 staging registers next to the 64 running sums) ptxas spills ~35
@@ -695,6 +725,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(gf + GEMPTY_OFF);   // one arrival per warp (256 per-thread arrivals on one mbarrier serialise)
+      if (st && warp == 8) trace_ev(p, 7, pgroup++);
       if (has_b) {
         if (g == 0) {
 #pragma unroll
@@ -782,9 +813,9 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 2) {
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
-      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * (e.corr_split ? 4 : 5);      // sempty, pfull: every converter thread
+      if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * (e.split4 ? 3 : (e.corr_split ? 4 : 5));      // sempty, pfull: every converter thread
       if (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES) count = 2;                    // bempty: the main and ONE correction issuer
-      if (i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) count = (p.halo && e.corr_split) ? 3 : 2;      // pempty: halo planes feed all taps
+      if (i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) count = !p.halo ? 2 : (e.split4 ? 4 : (e.corr_split ? 3 : 2));      // pempty: halo planes feed all taps
       if (i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2) count = e.corr_split ? 2 : 1;   // cfull
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
         count = T32_EPI_WARPS;                                                    // gempty, cempty: one arrival per promotion warp
@@ -798,6 +829,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (p.epi_t == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY.m[0]) : "memory");
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync()), "r"(0u) : "memory");
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync() + 4u), "r"(0u) : "memory");
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rg.issue_sync() + 8u), "r"(0u) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rg.tmem_slot()), "r"((uint32_t)TMEM_COLS)
@@ -816,11 +848,13 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp < 8) {
     // producer / MMA / converter warpgroups give registers away, the two promotion warpgroups take them
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T32_REGS_LOW));
+    const int nissue = e.split4 ? 4 : (e.corr_split ? 3 : 2);      // issuer warps 1 .. nissue, then the converter warps
     if (warp == 0) producer32(p, e, rg, &tmA, &tmB);
-    else if (warp == 1) mma32_dispatch<0>(p, e, rg, tmem_base);
+    else if (warp == 1) { if (e.split4) mma32_dispatch<0, 0>(p, e, rg, tmem_base); else mma32_dispatch<0>(p, e, rg, tmem_base); }
     else if (warp == 2) { if (e.corr_split) mma32_dispatch<1, 0>(p, e, rg, tmem_base); else mma32_dispatch<1>(p, e, rg, tmem_base); }
     else if (warp == 3 && e.corr_split) mma32_dispatch<1, 1>(p, e, rg, tmem_base);
-    else converter32(p, e, rg, (int)threadIdx.x - (e.corr_split ? 128 : 96), e.corr_split ? 128 : 160);
+    else if (warp == 4 && e.split4) mma32_dispatch<0, 1>(p, e, rg, tmem_base);
+    else converter32(p, e, rg, (int)threadIdx.x - 32 * (1 + nissue), 32 * (7 - nissue));
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T32_REGS_HIGH));
     if (p.stats) {     // debugging aid (VPS_CONV_STATS=1): clocks of the generic path only
@@ -964,6 +998,14 @@ extern "C" int64_t vps_packed_tc32_bytes(int cout, int cin, int kh, int kw, int 
   return plane_elems(cout, cin, kh, kw) * 2 * T32_PLANES * nprob;
 }
 
+// device address of the saturation counter (library-internal: the correlation's operand split in corr_tc.cu reports into the
+// same flag)
+extern "C" unsigned int* vps_tc32_overflow_flag() {
+  unsigned int* p = nullptr;
+  if (cudaGetSymbolAddress((void**)&p, g_tc32_overflow) != cudaSuccess) return nullptr;
+  return p;
+}
+
 // number of converter / packing threads that met |value| > 65504 (or NaN) since the last reset; synchronises the device
 extern "C" int vps_tc32_overflow(int reset) {
   unsigned int v = 0;
@@ -1089,18 +1131,22 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   if (group_env < 0) { const char* ev = getenv("VPS_TC32_GROUP"); group_env = ev ? atoi(ev) : 1; }
   e.group = group_env < 1 ? 1 : group_env;
   { static int dbg_env = -1; if (dbg_env < 0) { const char* ev = getenv("VPS_TC32_DBG"); dbg_env = ev ? atoi(ev) : 0; } e.dbg = dbg_env; }
+  { static int sl_env = -1; if (sl_env < 0) { const char* ev = getenv("VPS_TC32_SLEEP"); sl_env = ev ? atoi(ev) : 0; } e.sleep_ns = sl_env; }
   {
     static int split_env = -1;
     // measured neutral (fat layers 0.605 -> 0.609 ms, thin layers +2 %): the corrections issuer is not the pacing role; off
-    if (split_env < 0) { const char* ev = getenv("VPS_TC32_SPLIT"); split_env = ev ? atoi(ev) : 0; }
-    e.corr_split = (split_env && p.cin_chunks * ntaps >= 2) ? 1 : 0;
+    if (split_env < 0) { const char* ev = getenv("VPS_TC32_SPLIT"); split_env = ev ? atoi(ev) : 2; }
+    e.corr_split = ((split_env & 1) && p.cin_chunks * ntaps >= 2) ? 1 : 0;
+    // four issuer warps (halo layers only: the flat layers need their five converter warps): see mma32
+    e.split4 = ((split_env & 2) && halo && e.group == 1 && p.cin_chunks * ntaps >= 4) ? 1 : 0;
+    if (e.split4) e.corr_split = 1;
   }
   e.buf_cols = block_n <= 64 ? 64 : 128;
   // 128-column buffers: long tiles want a third group buffer (slack for the promotion latency), short tiles (1x1 layers
   // with few K steps) a second correction buffer so that the next tile can start while this one is stored
   const bool short_tile = p.cin_chunks * ntaps <= 6;
-  e.nmain = block_n <= 64 ? 6 : (short_tile ? 2 : 3);
-  e.ncorr = block_n <= 64 ? 2 : (short_tile ? 2 : 1);
+  e.nmain = block_n <= 64 ? 6 : ((short_tile || e.split4) ? 2 : 3);
+  e.ncorr = block_n <= 64 ? 2 : ((short_tile || e.split4) ? 2 : 1);
   p.nprob = nprob;
   p.tiles_per_prob = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
   p.total_tiles = p.tiles_per_prob * nprob;
@@ -1182,10 +1228,19 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
     smem_set = true;
   }
   const int grid = p.total_tiles < g_num_sms32 ? p.total_tiles : g_num_sms32;
+  static int trace_env = -1;
+  static long long* trace_buf = nullptr;
+  if (trace_env < 0) { const char* ev = getenv("VPS_CONV_TRACE"); trace_env = ev ? atoi(ev) : 0; }
+  p.trace = nullptr;
   if (stats_env) {   // debugging aid: per-role barrier-wait clocks, printed after a device sync (never on in production)
     if (!stats_buf) cudaMalloc(&stats_buf, sizeof(long long) * 8 * 1024);
     cudaMemsetAsync(stats_buf, 0, sizeof(long long) * 8 * grid, (cudaStream_t)stream);
     p.stats = stats_buf;
+    if (trace_env) {
+      if (!trace_buf) cudaMalloc(&trace_buf, sizeof(long long) * 8 * 256);
+      cudaMemsetAsync(trace_buf, 0, sizeof(long long) * 8 * 256, (cudaStream_t)stream);
+      p.trace = trace_buf;
+    }
   }
   static int pdl_env = -1;
   if (pdl_env < 0) { const char* ev = getenv("VPS_PDL"); pdl_env = ev ? atoi(ev) : 1; }
@@ -1211,6 +1266,18 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
             "(%.0f per step) | mma waits: group-buf %.0f planes %.0f weights %.0f corr-buf %.0f | promo: wait gfull %.0f store %.0f\n",
             a->kh, a->kw, a->sh, a->cin, a->cout, a->oh, a->ow, p.halo, block_n, e.group, p.a_stages, p.b_stages, tiles_cta, steps, m[4],
             m[4] / (tiles_cta * steps), m[0], m[1], m[2], m[3], m[5], m[6]);
+    if (p.trace) {
+      static long long t[8 * 256];
+      cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost);
+      // steady-state window: steps 40..71 of CTA 0, relative to the main issuer's MMA issue of step 40
+      const long long z = t[3 * 256 + 40];
+      fprintf(stderr, "trace (CTA 0, clocks relative to main issue of step 40): step | producer-B-issue | main: group-buf ok, weights ok, "
+                      "issued | corr: ready, issued | promo: group seen, released\n");
+      for (int sidx = 40; sidx < 72 && sidx < steps * tiles_cta; ++sidx)
+        fprintf(stderr, "  %3d | %7lld | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld\n", sidx, t[0 * 256 + sidx] - z, t[1 * 256 + sidx] - z,
+                t[2 * 256 + sidx] - z, t[3 * 256 + sidx] - z, t[4 * 256 + sidx] - z, t[5 * 256 + sidx] - z, t[6 * 256 + sidx] - z,
+                t[7 * 256 + sidx] - z);
+    }
   }
   return VPS_OK;
 }
@@ -1224,7 +1291,8 @@ extern "C" int vps_conv2d_tc32(const vps_conv_args* a, void* stream) { return vp
 extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offset, const void* w, int cout, const vps_tensor* y,
                                     void* stream) {
   VPS_CHECK_ARG(x->dtype == VPS_F32 && offset->dtype == VPS_F32 && offset->c >= 18, "deform_conv_tc32: dtypes");
-  VPS_CHECK_ARG(x->c % T32_KC == 0 && x->cs % 4 == 0 && ((uintptr_t)x->ptr & 15) == 0, "deform_conv_tc32: x must have cin %% 32 == 0");
+  VPS_CHECK_ARG(x->c % T32_KC == 0 && x->cs % 8 == 0 && ((uintptr_t)x->ptr & 31) == 0,
+                "deform_conv_tc32: x must have cin %% 32 == 0 and 32-byte aligned pixel rows (256-bit sampling loads)");
   VPS_CHECK_ARG(offset->n == x->n && offset->h == x->h && offset->w == x->w && y->n == x->n && y->h == x->h && y->w == x->w &&
                     y->c == cout, "deform_conv_tc32: shapes");
   VPS_CHECK_ARG((int64_t)x->n * x->h * x->w * x->cs < (1ll << 31), "deform_conv_tc32: tensor too large for 32-bit offsets");

@@ -33,6 +33,7 @@ struct ConvTcParams {
   int nk_last;                // K16 slabs of the last channel chunk that hold real channels (the rest is zero padding)
   int total_tiles;
   long long* stats;           // optional [grid][8] clock counters (VPS_CONV_STATS=1), else NULL
+  long long* trace;           // optional [8][256] event clocks of CTA 0's first 256 K steps (VPS_CONV_TRACE=1, tc32 kernel), else NULL
   void* y;
   int y_h, y_w, y_cs, y_dtype, y_vec;
   int oy_mul, oy_off, ox_mul, ox_off;

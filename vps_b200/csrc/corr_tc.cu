@@ -16,6 +16,7 @@
 //   warp 1: TMEM alloc + tcgen05.mma issue (M=128, N=96, K=16), accumulators double-buffered
 //   warps 2-9: epilogue, warp -> neighbourhood row 4*block + (warp % 4); the two warps of a row split the output rows
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -34,6 +35,9 @@ struct CorrParams {
   int n_img;
   void* out; int out_cs, out_dtype;
   int act; float slope;
+  float scale;        // result = accumulator * scale (1/C; the correction passes of the fp32-parity mode carry 2^-11 as well)
+  int accumulate;     // 1: add to the fp32 value already in `out` before the activation
+  int f16;            // 1: fp16 operands (the split planes of fp32 features), 0: bf16
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -181,7 +185,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPIX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t fmt = p.f16 ? 0u : ((1u << 7) | (1u << 10));       // A / B format: 0 = f16, 1 = bf16
+      const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(NPIX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int bsel = 0; uint32_t bphase = 0;
       int acc = 0; uint32_t aphase = 0;
@@ -216,7 +221,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     int acc = 0; uint32_t aphase = 0;
-    const float inv_c = 1.0f / (float)p.C;
+    const float inv_c = p.scale;
     auto load_row = [&](uint32_t t_row, int i, uint32_t* r) {
       if constexpr (TW == 12) { tmem_ld<8>(t_row + i * TW, r); tmem_ld<4>(t_row + i * TW + 8, r + 8); }
       else { tmem_ld<16>(t_row + i * TW, r); tmem_ld<8>(t_row + i * TW + 16, r + 16); }
@@ -242,8 +247,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__
             const int x = x0 + px + j * S2;
             if (ti >= 0 && ti < D && x < p.W) {
               float v = __uint_as_float(r[j]) * inv_c;
-              if (p.act == VPS_ACT_LRELU) v = v > 0.f ? v : v * p.slope;
               const int64_t o = rowb + (int64_t)x * p.out_cs - j;
+              if (p.accumulate) v += ((const float*)p.out)[o];
+              if (p.act == VPS_ACT_LRELU) v = v > 0.f ? v : v * p.slope;
               if (p.out_dtype == VPS_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(v);
               else ((float*)p.out)[o] = v;
             }
@@ -291,7 +297,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 template <int R, int S2>
-int launch(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int act, float slope, cudaStream_t st) {
+int launch(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int act, float slope, cudaStream_t st,
+           float scale = 0.f, int accumulate = 0, int f16 = 0) {
   constexpr int TW = 32 - 2 * R, TH = NPIX / TW;
   auto encode = get_encode();
   if (!encode) { vps::set_error("cuTensorMapEncodeTiled unavailable"); return VPS_E_CUDA; }
@@ -307,6 +314,7 @@ int launch(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, in
   p.tiles_x = vps::cdiv(vps::cdiv(f1->w, S2), TW);
   p.total_tiles = p.tiles_y * p.tiles_x * S2 * S2 * f1->n;
   p.out = out->ptr; p.out_cs = out->cs; p.out_dtype = out->dtype; p.act = act; p.slope = slope;
+  p.scale = scale != 0.f ? scale : 1.0f / (float)f1->c; p.accumulate = accumulate; p.f16 = f16;
   CUtensorMap tm1, tm2;
   for (int which = 0; which < 2; ++which) {
     const vps_tensor* t = which == 0 ? f1 : f2;
@@ -315,7 +323,7 @@ int launch(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, in
     cuuint32_t box1[4] = {KC, (cuuint32_t)(TW * S2), (cuuint32_t)(TH * S2), 1};
     cuuint32_t box2[4] = {KC, (cuuint32_t)(32 * S2), (cuuint32_t)(4 * S2), 1};
     cuuint32_t estr[4] = {1, S2, S2, 1};
-    CUresult r = encode(which == 0 ? &tm1 : &tm2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides,
+    CUresult r = encode(which == 0 ? &tm1 : &tm2, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides,
                         which == 0 ? box1 : box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vps::set_error("correlation_tc: tensor map encode failed (%d)", (int)r); return VPS_E_CUDA; }
@@ -336,7 +344,85 @@ int launch(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, in
   return VPS_OK;
 }
 
+// fp32 features -> two fp16 planes (dense NHWC, cs = c):  hi = fp16(v),  lo = fp16(2^11 * (v - hi))  -- the operand split of the
+// fp32-parity convolutions (conv_tc32.cu): v = hi + 2^-11 * lo to ~2^-22 relative
+__global__ void split_f16_planes_kernel(const float* __restrict__ x, int64_t npix, int c, int cs, __half* __restrict__ hi,
+                                        __half* __restrict__ lo, unsigned int* overflow) {
+  const int64_t total = npix * (c / 4);
+  bool over = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / (c / 4);
+    const int c4 = (int)(i - pix * (c / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + pix * cs + c4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned short hb, lb;
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hb) : "f"(vv[k]));
+      over = over || !(fabsf(vv[k]) <= 65504.f);
+      const float r = (vv[k] - __half2float(__ushort_as_half(hb))) * 2048.f;
+      asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(lb) : "f"(r));
+      h[k] = __ushort_as_half(hb); l[k] = __ushort_as_half(lb);
+    }
+    *reinterpret_cast<uint2*>(hi + pix * c + c4) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + pix * c + c4) = *reinterpret_cast<const uint2*>(l);
+  }
+  if (over && overflow) atomicAdd(overflow, 1u);
+}
+
 }  // namespace
+
+extern "C" unsigned int* vps_tc32_overflow_flag();      // conv_tc32.cu: device address of the saturation counter
+
+extern "C" int64_t vps_correlation_tc32_ws_bytes(const vps_tensor* f1) {
+  return 4 * (int64_t)f1->n * f1->h * f1->w * f1->c * 2 + 1024;
+}
+
+// Correlation of fp32 features on the tensor cores in the parity precision: both maps are split into fp16 planes
+// (v = hi + 2^-11 lo) and the banded GEMM runs three times, hi.hi, then hi.lo and lo.hi scaled by 2^-11 and accumulated
+// into the fp32 output (the activation is applied by the last pass).  Unlike the stacked convolutions a correlation is a
+// single K = C <= 256 contraction (16 MMAs per accumulator chain) whose result is not fed through further layers of the same
+// kind, so the tensor core's truncating accumulation (~3e-7 relative over such a chain) needs no promotion here.
+// `ws`: vps_correlation_tc32_ws_bytes() of scratch, 256-byte aligned.  Same supported geometries as vps_correlation_tc.
+extern "C" int vps_correlation_tc32(const vps_tensor* f1, const vps_tensor* f2, const vps_tensor* out, int pad, int max_disp,
+                                    int stride1, int stride2, int act, float slope, void* ws, void* stream) {
+  VPS_CHECK_ARG(stride1 == 1 && pad == max_disp, "correlation_tc32: only stride1=1, pad==max_displacement");
+  VPS_CHECK_ARG(f1->dtype == VPS_F32 && f2->dtype == VPS_F32 && out->dtype == VPS_F32, "correlation_tc32: fp32 tensors only");
+  VPS_CHECK_ARG(f1->h == f2->h && f1->w == f2->w && f1->c == f2->c && f1->n == f2->n && out->h == f1->h && out->w == f1->w,
+                "correlation_tc32: shape mismatch");
+  VPS_CHECK_ARG(f1->c % KC == 0 && f1->c <= KC * MAX_KCH, "correlation_tc32: C must be a multiple of 64, <= 256");
+  VPS_CHECK_ARG(f1->cs % 4 == 0 && f2->cs % 4 == 0 && ((uintptr_t)f1->ptr & 15) == 0 && ((uintptr_t)f2->ptr & 15) == 0 &&
+                    ws && ((uintptr_t)ws & 255) == 0, "correlation_tc32: features / scratch must be aligned");
+  VPS_CHECK_ARG(act == VPS_ACT_NONE || act == VPS_ACT_LRELU, "correlation_tc32: act");
+  const int R = max_disp / stride2, D = 2 * R + 1;
+  VPS_CHECK_ARG(out->c == D * D, "correlation_tc32: out.c %d != %d", out->c, D * D);
+  VPS_CHECK_ARG((R == 10 && stride2 == 2) || (R == 4 && stride2 == 1), "correlation_tc32: unsupported (max_disp %d, stride2 %d)",
+                max_disp, stride2);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t npix = (int64_t)f1->n * f1->h * f1->w, plane = npix * f1->c;
+  __half* base = (__half*)ws;
+  vps_tensor t[4];      // f1 hi, f1 lo, f2 hi, f2 lo
+  for (int i = 0; i < 4; ++i) {
+    t[i] = *f1; t[i].ptr = base + i * plane; t[i].cs = f1->c; t[i].dtype = VPS_BF16;      // (2-byte elements; the kernel is told f16)
+  }
+  unsigned int* flag = vps_tc32_overflow_flag();
+  const int blocks = (int)((npix * (f1->c / 4) + 255) / 256 > 8192 ? 8192 : (npix * (f1->c / 4) + 255) / 256);
+  split_f16_planes_kernel<<<blocks, 256, 0, st>>>((const float*)f1->ptr, npix, f1->c, f1->cs, base, base + plane, flag);
+  VPS_CUDA_LAST("split_f16_planes");
+  split_f16_planes_kernel<<<blocks, 256, 0, st>>>((const float*)f2->ptr, npix, f1->c, f2->cs, base + 2 * plane, base + 3 * plane, flag);
+  VPS_CUDA_LAST("split_f16_planes");
+  const float s1 = 1.0f / (float)f1->c, s2 = s1 * (1.0f / 2048.0f);
+  int rc;
+#define CORR_PASS(A, B, SC, ACC, ACT)                                                                        \
+  rc = (R == 10) ? launch<10, 2>(&t[A], &t[B], out, ACT, slope, st, SC, ACC, 1) : launch<4, 1>(&t[A], &t[B], out, ACT, slope, st, SC, ACC, 1); \
+  if (rc != VPS_OK) return rc;
+  CORR_PASS(0, 2, s1, 0, VPS_ACT_NONE)      // f1.hi x f2.hi
+  CORR_PASS(0, 3, s2, 1, VPS_ACT_NONE)      // f1.hi x f2.lo
+  CORR_PASS(1, 2, s2, 1, act)               // f1.lo x f2.hi, then the activation
+#undef CORR_PASS
+  return VPS_OK;
+}
 
 // Tensor-core correlation; returns VPS_E_ARG (without launching) when the geometry is not one of the two supported
 // call sites -- vps_correlation then uses the CUDA-core kernel.

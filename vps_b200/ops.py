@@ -270,12 +270,25 @@ def conv2d_tc_multi(x, pws, y, pads, omaps, act=ACT_NONE, slope=0.1, out_scale=1
 
 # ------------------------------------------------------------------ FlowNet2 native ops
 def correlation(f1, f2, out, pad, max_disp, stride1, stride2, act=ACT_NONE, slope=0.1, impl=None):
-    """impl: None = dispatch (tensor cores for bf16 features), "tc" / "simt" force one implementation."""
-    fn = {None: "vps_correlation", "tc": "vps_correlation_tc", "simt": "vps_correlation_simt"}[impl]
+    """impl: None = dispatch (tensor cores for bf16 features, and for fp32 features in the tc32 precision), "tc" / "tc32" /
+    "simt" force one implementation."""
+    fn = {None: "vps_correlation", "tc": "vps_correlation_tc", "simt": "vps_correlation_simt", "tc32": "vps_correlation_tc32"}[impl]
     if PROFILE is not None:
         d = 2 * (max_disp // stride2) + 1
         _NOTE["flops"] = 2 * f1.shape[0] * f1.shape[1] * f1.shape[2] * f1.shape[3] * d * d
         _NOTE["tag"] = "corr d%d s%d C%d @%dx%d" % (max_disp, stride2, f1.shape[3], f1.shape[1], f1.shape[2])
+    if impl is None and F32_TC[0] and f1.dtype == torch.float32 and f2.dtype == torch.float32 and out.dtype == torch.float32:
+        c = f1.shape[3]
+        # (the d4 / stride2 1 site runs 1.39 ms this way against 0.97 ms on the CUDA cores: its band is 9 of 32 columns wide)
+        if (c % 64 == 0 and c <= 256 and stride1 == 1 and pad == max_disp and (max_disp, stride2) == (20, 2)
+                and vt(f1).cs % 4 == 0 and vt(f2).cs % 4 == 0 and f1.data_ptr() % 16 == 0 and f2.data_ptr() % 16 == 0):
+            fn = "vps_correlation_tc32"
+    if fn == "vps_correlation_tc32":
+        ws = torch.empty(int(lib().vps_correlation_tc32_ws_bytes(C.byref(vt(f1)))), dtype=torch.uint8, device=f1.device)
+        off = (-ws.data_ptr()) % 256
+        check(lib().vps_correlation_tc32(C.byref(vt(f1)), C.byref(vt(f2)), C.byref(vt(out)), pad, max_disp, stride1, stride2,
+                                         act, C.c_float(slope), C.c_void_p(ws.data_ptr() + off), stream()), "correlation_tc32")
+        return out
     check(getattr(lib(), fn)(C.byref(vt(f1)), C.byref(vt(f2)), C.byref(vt(out)), pad, max_disp, stride1,
                                 stride2, act, C.c_float(slope), stream()), "correlation")
     return out
