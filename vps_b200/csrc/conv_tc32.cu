@@ -421,10 +421,12 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
   const int G = e.group, last_cc = p.cin_chunks - 1, a_stages = p.a_stages, b_stages = p.b_stages;
   const int nbuf = ROLE == 0 ? e.nmain : e.ncorr;
   const uint32_t buf0 = tmem_base + (ROLE == 0 ? 0u : (uint32_t)(e.nmain * e.buf_cols)), buf_cols = (uint32_t)e.buf_cols;
-  int as = 0, bs = 0, tb = 0;
+  // a split corrections warp accumulates the steps of its parity in its OWN correction buffer (index PAR; the promotion adds
+  // both): two warps feeding one accumulator would make the order of its truncating additions depend on their relative timing
+  int as = 0, bs = 0, tb = (ROLE == 1 && PAR > 0) ? PAR : 0;
   uint32_t aphase = 0, bphase = 0, tphase = 0;       // tphase: one parity bit per TMEM buffer of this role
   uint32_t nstep = 0;                                // K steps issued so far (all tiles)
-  const uint32_t sync_addr = rg.issue_sync(), sync2_addr = sync_addr + 8u;      // [main even | main odd], [corrections even]
+  const uint32_t sync_addr = rg.issue_sync();      // steps issued by the main-product warp(s): [even | odd]
   long long w_t = 0, w_a = 0, w_b = 0;
   const long long t_begin = STATS ? clock64() : 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -456,7 +458,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           if (STATS) w_t += clock64() - t0;
           if (STATS && ROLE == 0) trace_ev(p, 1, nstep - 1u);
           d_tmem = buf0 + (uint32_t)tb * buf_cols;
-          first = (ROLE == 1 && PAR == 1) ? 1u : 0u;       // the odd warp never starts the tile's accumulation
+          first = 0;
           tile_waited = true;
         }
         if (HALO ? (tap == 0) : true) a16 = a_base16 + (uint32_t)as * a_bytes16;
@@ -467,8 +469,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
         if (ROLE == 1) {
           // the tensor pipe executes MMAs in issue order: a correction issuer that ran ahead (it never waits for a group
           // buffer) would queue several steps of its 4-MMA batches in front of the main product and stretch the latency of
-          // every promoted group -- it issues step s only after the main-product warp has issued step s; the odd warp also
-          // follows the even warp's previous step (whose first MMA of a tile resets the accumulator).  This comes BEFORE the
+          // every promoted group -- it issues step s only after the main-product warp has issued step s.  This comes BEFORE the
           // barrier waits: a warp that skips every other use of a ring slot re-visits the slot's barrier two phases later with
           // the same parity, and only the fact that the main warp (which waits on every phase) is already past this step
           // makes that wait unambiguous.
@@ -477,11 +478,6 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           do {
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(main_ctr) : "memory");
           } while ((int32_t)(seen - nstep) < 0);
-          if (PAR == 1) {
-            do {
-              asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(sync2_addr) : "memory");
-            } while ((int32_t)(seen - (nstep - 1u)) < 0);
-          }
         }
         if (HALO ? !a_waited : true) {
           const long long t0 = STATS ? clock64() : 0;
@@ -516,7 +512,6 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
             if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + b_plane16 + 2, b_hi, idesc, 1u);
             }
           }
-          if (ROLE == 1 && PAR == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sync2_addr), "r"(nstep) : "memory");
           umma_commit(rg.bempty(bs));
           if (my_item_done) umma_commit(rg.pempty(as));
           if (ROLE == 0 ? close : my_last_step) umma_commit(ROLE == 0 ? rg.gfull(tb) : rg.cfull(tb));
@@ -525,7 +520,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
         if (STATS && mine) trace_ev(p, ROLE == 0 ? 3 : 5, nstep - 1u);
         if (close) {
           tphase ^= 1u << tb;
-          if (++tb == nbuf) tb = 0;
+          if (!(ROLE == 1 && PAR >= 0) && ++tb == nbuf) tb = 0;
           in_group = 0;
         }
         if (item_done) { if (++as == a_stages) { as = 0; aphase ^= 1; } }
@@ -738,7 +733,8 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
       gphase ^= 1u << gb;
       if (++gb == nmain_r) gb = 0;
     }
-    // ---- the tile's correction products
+    // ---- the tile's correction products (split corrections issuers: one buffer per issuer, both belong to this tile)
+    for (int cpass = 0; cpass < (e.corr_split ? 2 : 1); ++cpass) {
     const uint32_t cf = gfull0 + 8u * (2u * T32_MAX_MAIN) + 8u * cb;       // cfull(cb); cempty(cb) = cf + 16
     mbar_wait(cf, (cphase >> cb) & 1u);
     tc_fence_after();
@@ -765,6 +761,7 @@ __device__ __forceinline__ void promote_epilogue(const ConvTcParams& p, const Tc
     }
     cphase ^= 1u << cb;
     if (++cb == (uint32_t)e.ncorr) cb = 0;
+    }
     const long long t1 = st ? clock64() : 0;
     // ---- bias / activation / residual / store of this tile
     const int prob = tile / p.tiles_per_prob;
@@ -816,7 +813,6 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * (e.split4 ? 3 : (e.corr_split ? 4 : 5));      // sempty, pfull: every converter thread
       if (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES) count = 2;                    // bempty: the main and ONE correction issuer
       if (i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) count = !p.halo ? 2 : (e.split4 ? 4 : (e.corr_split ? 3 : 2));      // pempty: halo planes feed all taps
-      if (i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2) count = e.corr_split ? 2 : 1;   // cfull
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
         count = T32_EPI_WARPS;                                                    // gempty, cempty: one arrival per promotion warp
       mbar_init(rg.bar_base + 8u * i, count);
@@ -1136,10 +1132,9 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
     static int split_env = -1;
     // measured neutral (fat layers 0.605 -> 0.609 ms, thin layers +2 %): the corrections issuer is not the pacing role; off
     if (split_env < 0) { const char* ev = getenv("VPS_TC32_SPLIT"); split_env = ev ? atoi(ev) : 2; }
-    e.corr_split = ((split_env & 1) && p.cin_chunks * ntaps >= 2) ? 1 : 0;
     // four issuer warps (halo layers only: the flat layers need their five converter warps): see mma32
     e.split4 = ((split_env & 2) && halo && e.group == 1 && p.cin_chunks * ntaps >= 4) ? 1 : 0;
-    if (e.split4) e.corr_split = 1;
+    e.corr_split = e.split4;
   }
   e.buf_cols = block_n <= 64 ? 64 : 128;
   // 128-column buffers: long tiles want a third group buffer (slack for the promotion latency), short tiles (1x1 layers
