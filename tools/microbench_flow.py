@@ -37,7 +37,7 @@ for dt, name in ((torch.bfloat16, "bf16"), (torch.float32, "f32")):
     f1 = torch.randn(1, H, W, C, generator=g).to(dev).to(dt)
     f2 = torch.randn(1, H, W, C, generator=g).to(dev).to(dt)
     out = torch.empty(1, H, W, 448, dtype=dt, device=dev)[..., :441]
-    impls = ("tc", "simt") if dt == torch.bfloat16 else ("simt",)
+    impls = ("tc", "simt") if dt == torch.bfloat16 else ("tc32", "simt")     # tc32: split fp16 planes, 3 tensor-core passes
     for impl in impls:
         ms = timeit(lambda: ops.correlation(f1, f2, out, 20, 20, 1, 2, impl=impl))
         by = (2 * H * W * C + H * W * 441) * esz
