@@ -43,7 +43,10 @@ constexpr int T32_EPI_WARPS = 8;            // warps 8..15: two per TMEM lane qu
 constexpr int T32_CONV_WARPS = 5;           // warps 3..7 (warp 0 = TMA, warp 1 = main-product issuer, warp 2 = correction issuer;
                                             // VPS_TC32_SPLIT=1: warp 3 issues the corrections of the odd K steps, 4 converter warps)
 constexpr int T32_THREADS = 96 + 32 * (T32_EPI_WARPS + T32_CONV_WARPS);     // 512 = 4 warpgroups
-constexpr int T32_REGS_LOW = 64, T32_REGS_HIGH = 192;    // setmaxnreg: 256 * 64 + 256 * 192 = 65536
+// setmaxnreg: 256 * 80 + 256 * 176 = 65536.  The single-thread issue loops must not spill (every instruction of theirs is on the
+// kernel's critical path: with 64 registers ptxas kept a few values in local memory); the promotion fits 176 since its
+// epilogue became the TMA store (0 spill bytes in this kernel).
+constexpr int T32_REGS_LOW = 80, T32_REGS_HIGH = 176;
 constexpr int T32_KC = 32;                  // channels per K step: 64-byte operand rows (SWIZZLE_64B), 2 x K16
 constexpr int T32_MAX_N = 128;              // TMEM: block_n <= 64: 6 main (group) + 2 correction (tile) buffers of 64 columns,
                                             //       block_n <= 128: 3 main + 1 correction buffer of 128 columns
@@ -198,8 +201,7 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
                                            const CUtensorMap* tmB) {
   const int ntaps = p.kh * p.kw, kw = p.kw;
   const bool halo = p.halo != 0;
-  const int rowg = p.rowg > 1 ? p.rowg : 1;
-  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes, b_bytes = (uint32_t)(rowg * T32_PLANES) * (uint32_t)e.b_plane_bytes;
+  const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes, b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
   const int bn = p.block_n;
   int ss = 0, bs = 0;
   uint32_t sphase = 0, bphase = 0, pstep = 0;
@@ -220,16 +222,13 @@ __device__ __forceinline__ void producer32(const ConvTcParams& p, const Tc32Extr
           }
           if (++ss == T32_STAGE_SLOTS) { ss = 0; sphase ^= 1; }
         }
-        if (rowg == 1 || s == 0) {      // halo mode: the kw taps of a filter row share one ring slot and one barrier round
-          mbar_wait_relaxed(rg.bempty(bs), bphase ^ 1, (uint32_t)e.sleep_ns);
-          trace_ev(p, 0, pstep);
-          if (elect_one()) {     // both weight planes of the row's taps in one 5-D box {32 ch, bn, taps, 1, 2 planes}
-            mbar_expect_tx(rg.bfull(bs), b_bytes);
-            tma_load_5d(rg.b_base + bs * rg.b_bytes, tmB, rg.bfull(bs), cc * T32_KC, n0, tap, t.prob, 0);
-          }
-          if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
+        mbar_wait_relaxed(rg.bempty(bs), bphase ^ 1, (uint32_t)e.sleep_ns);
+        trace_ev(p, 0, pstep++);
+        if (elect_one()) {     // both weight planes of this (tap, chunk) in one 5-D box
+          mbar_expect_tx(rg.bfull(bs), b_bytes);
+          tma_load_5d(rg.b_base + bs * rg.b_bytes, tmB, rg.bfull(bs), cc * T32_KC, n0, tap, t.prob, 0);
         }
-        ++pstep;
+        if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
         if (++s == kw) { s = 0; ++r; }
       }
     }
@@ -419,8 +418,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
   const int ntaps = p.kh * p.kw, kw = p.kw;
   const uint32_t row_skip = HALO ? (uint32_t)(p.halo_w - kw) * 4u : 0u;          // descriptor units (16 B) to the next halo row
   const uint32_t a_hi = desc_hi32(HALO ? (uint32_t)p.halo_w * 64u : 512u), b_hi = desc_hi32(512u);
-  const int rowg = p.rowg > 1 ? p.rowg : 1;          // taps per weight ring slot (halo mode: a filter row)
-  const uint32_t a_plane16 = (uint32_t)e.plane_bytes >> 4, b_tap16 = (uint32_t)e.b_plane_bytes >> 4, b_plane16 = b_tap16 * (uint32_t)rowg;
+  const uint32_t a_plane16 = (uint32_t)e.plane_bytes >> 4, b_plane16 = (uint32_t)e.b_plane_bytes >> 4;
   const uint32_t a_bytes16 = rg.a_bytes >> 4, b_bytes16 = rg.b_bytes >> 4;
   const uint32_t a_base16 = (rg.a_base & 0x3FFFF) >> 4, b_base16 = (rg.b_base & 0x3FFFF) >> 4;
   const int G = e.group, last_cc = p.cin_chunks - 1, a_stages = p.a_stages, b_stages = p.b_stages;
@@ -442,8 +440,8 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
     for (int cc = 0; cc <= last_cc; ++cc) {
       const bool two = cc != last_cc || e.nk_last > 1;
       uint32_t a16 = 0;
-      int sx = 0, sb = 0;                    // tap inside the halo row / inside the weight slot
-      bool a_waited = false, b_waited = false;
+      int sx = 0;
+      bool a_waited = false;
       for (int tap = 0; tap < ntaps; ++tap, par ^= 1u) {
         const bool last_step = cc == last_cc && tap == ntaps - 1;
         // ownership: corrections by the parity of the step inside the tile (step 0 resets the tile's accumulator), the main
@@ -490,20 +488,16 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           if (STATS) w_a += clock64() - t0;
           a_waited = true;
         }
-        if (!b_waited) {                     // first tap of the weight slot issued by this warp
+        {
           const long long t0 = STATS ? clock64() : 0;
           mbar_wait(rg.bfull(bs), bphase);
           if (STATS) w_b += clock64() - t0;
-          b_waited = true;
+          if (STATS) trace_ev(p, ROLE == 0 ? 2 : 4, nstep - 1u);
         }
-        if (STATS) trace_ev(p, ROLE == 0 ? 2 : 4, nstep - 1u);
         tc_fence_after();
         }
         const bool close = ROLE == 0 ? (++in_group == G || last_step) : last_step;
-        const uint32_t b16 = b_base16 + (uint32_t)bs * b_bytes16 + (uint32_t)sb * b_tap16;
-        // last tap of this weight slot issued by this warp: its commit hands the slot back to the producer
-        const bool slot_done = sb == rowg - 1;
-        const bool my_slot_done = PAR < 0 ? slot_done : (slot_done ? mine : (mine && sb == rowg - 2));
+        const uint32_t b16 = b_base16 + (uint32_t)bs * b_bytes16;
         if (mine && elect_one()) {
           if (ROLE == 0) {                 // main: A x B
             if (!(e.dbg & 4)) {
@@ -521,7 +515,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
             if (two) umma_f16_lohi(d_tmem, a16 + 2, a_hi, b16 + b_plane16 + 2, b_hi, idesc, 1u);
             }
           }
-          if (my_slot_done) umma_commit(rg.bempty(bs));
+          umma_commit(rg.bempty(bs));
           if (my_item_done) umma_commit(rg.pempty(as));
           if (ROLE == 0 ? close : my_last_step) umma_commit(ROLE == 0 ? rg.gfull(tb) : rg.cfull(tb));
         }
@@ -533,7 +527,7 @@ __device__ __forceinline__ void mma32(const ConvTcParams& p, const Tc32Extra& e,
           in_group = 0;
         }
         if (item_done) { if (++as == a_stages) { as = 0; aphase ^= 1; } }
-        if (slot_done) { sb = 0; b_waited = false; if (++bs == b_stages) { bs = 0; bphase ^= 1; } } else ++sb;
+        if (++bs == b_stages) { bs = 0; bphase ^= 1; }
         if (HALO) {                        // next tap: one pixel (64 B = 4 units) to the right, or the start of the next halo row
           a16 += 4u;
           if (++sx == kw) { sx = 0; a16 += row_skip; }
@@ -811,8 +805,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   Ring32 rg;
   rg.s_base = smem_base; rg.s_bytes = (uint32_t)e.stage_bytes;
   rg.a_base = rg.s_base + T32_STAGE_SLOTS * rg.s_bytes; rg.a_bytes = (uint32_t)T32_PLANES * (uint32_t)e.plane_bytes;
-  rg.b_base = rg.a_base + (uint32_t)p.a_stages * rg.a_bytes;
-  rg.b_bytes = (uint32_t)((p.rowg > 1 ? p.rowg : 1) * T32_PLANES) * (uint32_t)e.b_plane_bytes;
+  rg.b_base = rg.a_base + (uint32_t)p.a_stages * rg.a_bytes; rg.b_bytes = (uint32_t)T32_PLANES * (uint32_t)e.b_plane_bytes;
   const uint32_t scratch_base = rg.b_base + (uint32_t)p.b_stages * rg.b_bytes;      // 8 x 4 KB epilogue scratch (epi_t == 2)
   rg.bar_base = scratch_base + (p.epi_t == 2 ? T32_SCRATCH_BYTES : 0u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -821,7 +814,7 @@ conv_igemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = lane; i < T32_NBAR; i += 32) {
       uint32_t count = 1;
       if (i >= MAX_STAGES && i < 3 * MAX_STAGES) count = 32 * (e.split4 ? 3 : (e.corr_split ? 4 : 5));      // sempty, pfull: every converter thread
-      if (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES) count = (e.split4 && p.rowg > 1) ? 4 : 2;     // bempty: every issuer warp that reads the slot
+      if (i >= 5 * MAX_STAGES && i < 6 * MAX_STAGES) count = 2;                    // bempty: the main and ONE correction issuer
       if (i >= 3 * MAX_STAGES && i < 4 * MAX_STAGES) count = !p.halo ? 2 : (e.split4 ? 4 : (e.corr_split ? 3 : 2));      // pempty: halo planes feed all taps
       if ((i >= 6 * MAX_STAGES + T32_MAX_MAIN && i < 6 * MAX_STAGES + 2 * T32_MAX_MAIN) || i >= 6 * MAX_STAGES + 2 * T32_MAX_MAIN + 2)
         count = T32_EPI_WARPS;                                                    // gempty, cempty: one arrival per promotion warp
@@ -1108,12 +1101,6 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   }
   const int smem_budget = 227 * 1024 - 1024 - T32_BAR_BYTES - 64 - (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
   const int a_side = T32_STAGE_SLOTS * e.stage_bytes + p.a_stages * p.a_stage_bytes;
-  // halo mode: the kw taps of a filter row share a weight ring slot (one barrier round trip per row instead of per tap: a
-  // satisfied mbarrier wait costs the issuing thread 300-500 clocks, §7 of DESIGN.md)
-  static int rowg_env = -1;
-  if (rowg_env < 0) { const char* ev = getenv("VPS_TC32_ROWG"); rowg_env = ev ? atoi(ev) : 1; }
-  const int rowg = (halo && rowg_env && a->kw >= 2) ? a->kw : 1;
-  p.rowg = rowg;
   // N tile: divisor of cout_pad (multiple of 16, <= 128) minimising waves * (steps * step clocks + epilogue); a step is
   // 6 MMAs = 3*bn clocks at the MMA floor, ~300 clocks of issue / barrier latency, or its weight bytes at the L2 rate
   int block_n = 16;
@@ -1122,7 +1109,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
     double best = -1.0;
     for (int bn = 16; bn <= T32_MAX_N && bn <= cout_pad; bn += 16) {
       if (cout_pad % bn) continue;
-      if (a_side + 2 * rowg * bn * 64 * T32_PLANES > smem_budget) continue;
+      if (a_side + 2 * bn * 64 * T32_PLANES > smem_budget) continue;
       // TMA-store epilogue: boxes are 32 channels wide and only clipped at the END of the tensor's channel axis
       if (p.epi_t == 2 && (bn % 32) && bn != cout_pad) continue;
       const int64_t tiles = m_tiles * (cout_pad / bn);
@@ -1135,7 +1122,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
   e.b_plane_bytes = block_n * 64;
   {
-    int bst = (smem_budget - a_side) / (rowg * T32_PLANES * e.b_plane_bytes);
+    int bst = (smem_budget - a_side) / (T32_PLANES * e.b_plane_bytes);
     p.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
     VPS_CHECK_ARG(p.b_stages >= 2, "conv2d_tc32: ring does not fit (%d x %d px halo, bn %d)", halo_h, p.halo_w, block_n);
   }
@@ -1202,7 +1189,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
     cuuint64_t dims[5] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)ntaps, (cuuint64_t)nprob, T32_PLANES};
     cuuint64_t strides[4] = {(cuuint64_t)ntaps * cin_pad * 2, (cuuint64_t)cin_pad * 2, (cuuint64_t)n_plane * 2,
                              (cuuint64_t)n_plane * nprob * 2};
-    cuuint32_t box[5] = {(cuuint32_t)T32_KC, (cuuint32_t)block_n, (cuuint32_t)rowg, 1, T32_PLANES};
+    cuuint32_t box[5] = {(cuuint32_t)T32_KC, (cuuint32_t)block_n, 1, 1, T32_PLANES};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, (void*)a->w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1229,7 +1216,7 @@ extern "C" int vps_conv2d_tc32_multi(const vps_conv_args* args, int nprob, void*
       }
     }
   }
-  const int smem = a_side + p.b_stages * rowg * T32_PLANES * e.b_plane_bytes + 1024 + T32_BAR_BYTES + (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
+  const int smem = a_side + p.b_stages * T32_PLANES * e.b_plane_bytes + 1024 + T32_BAR_BYTES + (p.epi_t == 2 ? (int)T32_SCRATCH_BYTES : 0);
   static bool smem_set = false;
   if (!smem_set) {
     if (cudaFuncSetAttribute(conv_igemm_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -1334,7 +1321,7 @@ extern "C" int vps_deform_conv_tc32(const vps_tensor* x, const vps_tensor* offse
   while (block_n > T32_MAX_N || cout_pad % block_n) block_n -= 16;
   VPS_CHECK_ARG(block_n % 32 == 0 || block_n == cout_pad, "deform_conv_tc32: cout %d has no N tile the TMA epilogue can store", cout);
   p.block_n = block_n; p.n_tiles_n = cout_pad / block_n;
-  p.kh = p.kw = 3; p.sh = p.sw = 1; p.halo = 0; p.halo_w = 0; p.rowg = 1;
+  p.kh = p.kw = 3; p.sh = p.sw = 1; p.halo = 0; p.halo_w = 0;
   p.cin_chunks = x->c / T32_KC;
   e.rows = BLOCK_M; e.dcn = 1;
   e.plane_bytes = BLOCK_M * 64; e.stage_bytes = 0; e.nk_last = 2;
